@@ -1,0 +1,22 @@
+#!/usr/bin/env bash
+# Builds libvp8r.so (host parser + runtime + sm_100a kernels) in-tree, the synthetic-stream
+# tool, and the test-only oracle.  nvcc cross-compiles without a GPU.
+set -euo pipefail
+cd "$(dirname "$0")"
+OUT=vp8_b200/_lib
+mkdir -p "$OUT" vp8_b200/_build
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+CXXFLAGS="-O3 -std=c++17 -Iinclude -Ivp8_b200/csrc"
+$NVCC $ARCH -lineinfo $CXXFLAGS -Xcompiler -fPIC,-fvisibility=hidden -c vp8_b200/csrc/cuda/recon_kernels.cu -o vp8_b200/_build/recon_kernels.o
+$NVCC $ARCH -lineinfo $CXXFLAGS -Xcompiler -fPIC,-fvisibility=hidden -c vp8_b200/csrc/rt/engine.cu -o vp8_b200/_build/engine.o
+g++ $CXXFLAGS -fPIC -fvisibility=hidden -Wall -Wextra -c vp8_b200/csrc/host/frame_parser.cc -o vp8_b200/_build/frame_parser.o
+g++ $CXXFLAGS -fPIC -fvisibility=hidden -Wall -Wextra -c vp8_b200/csrc/capi.cc -o vp8_b200/_build/capi.o
+$NVCC $ARCH -shared -o "$OUT/libvp8r.so" vp8_b200/_build/recon_kernels.o vp8_b200/_build/engine.o \
+    vp8_b200/_build/frame_parser.o vp8_b200/_build/capi.o
+if [ -f tools/vp8synth.cc ]; then
+  g++ -O2 -std=c++17 -Wall -Wextra tools/vp8synth.cc -o "$OUT/vp8synth"
+fi
+make -s -C oracle oracle
+if [ "${SKIP_REF:-0}" != "1" ]; then make -s -C oracle ref; fi
+echo "built $OUT/libvp8r.so"

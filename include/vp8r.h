@@ -176,9 +176,11 @@ VP8R_API int vp8r_read_batch(vp8r_engine *e, int n, vp8r_stream *const *streams,
                              uint8_t *const *dst, const size_t *cap, int async);
 VP8R_API int vp8r_stream_read_frame(vp8r_stream *s, uint8_t *dst, size_t cap);
 
-/* Device-side checksum of the cropped I420 image (Adler-style pair folded into 64 bits),
- * for parity checks at sizes where copying every frame back would dominate. */
+/* Device-side checksum of the cropped I420 image: low word sum(b_i), high word
+ * sum((i+1)*b_i), both mod 2^32, i = byte index in the Y,U,V stream.  For parity checks at sizes
+ * where copying every frame back would dominate. */
 VP8R_API int vp8r_stream_checksum(vp8r_stream *s, uint64_t *out);
+VP8R_API int vp8r_checksum_batch(vp8r_engine *e, int n, vp8r_stream *const *streams, uint64_t *out);
 /* Same checksum computed on host memory holding a cropped I420 image. */
 VP8R_API uint64_t vp8r_checksum_i420(const uint8_t *i420, int width, int height);
 

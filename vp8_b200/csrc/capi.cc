@@ -1,0 +1,70 @@
+// Host-only part of the C ABI: parser, parsed-frame objects, checksums, error reporting.
+// (The engine half lives in rt/engine.cu.)
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "host/frame_parser.h"
+#include "host/parsed_frame.h"
+#include "rt/error.h"
+#include "vp8r.h"
+
+namespace vp8r {
+namespace {
+thread_local std::string g_error;
+}
+void SetError(const std::string &msg) { g_error = msg; }
+const char *LastError() { return g_error.c_str(); }
+}  // namespace vp8r
+
+extern "C" {
+
+VP8R_API const char *vp8r_last_error(void) { return vp8r::LastError(); }
+VP8R_API const char *vp8r_version(void) { return "vp8r 0.1 (sm_100a)"; }
+
+VP8R_API vp8r_parser *vp8r_parser_create(void) { return new (std::nothrow) vp8r_parser(); }
+VP8R_API void vp8r_parser_destroy(vp8r_parser *p) { delete p; }
+VP8R_API void vp8r_parser_reset(vp8r_parser *p) {
+  if (p) p->impl.Reset();
+}
+
+VP8R_API vp8r_frame *vp8r_frame_create(int pinned) {
+  vp8r_frame *f = new (std::nothrow) vp8r_frame();
+  if (f) f->pinned = pinned != 0;
+  return f;
+}
+VP8R_API void vp8r_frame_destroy(vp8r_frame *f) { delete f; }
+
+VP8R_API int vp8r_frame_get_desc(const vp8r_frame *f, vp8r_frame_desc *out) {
+  if (!f || !out || !f->blob) return VP8R_ERR_INVALID_ARG;
+  out->hdr = f->hdr;
+  out->mbs = f->mbs();
+  out->payload = f->payload();
+  return VP8R_OK;
+}
+
+VP8R_API int vp8r_parser_parse(vp8r_parser *p, const uint8_t *data, size_t size, vp8r_frame *out) {
+  if (!p || !out) return VP8R_ERR_INVALID_ARG;
+  int rc = p->impl.Parse(data, size, out);
+  if (rc != VP8R_OK) vp8r::SetError(p->impl.error());
+  return rc;
+}
+
+VP8R_API int vp8r_is_key_frame(const uint8_t *data, size_t size) {
+  return (data && size >= 1) ? !(data[0] & 1) : 0;
+}
+
+// s1 = sum(b_i), s2 = sum((i+1) * b_i), both mod 2^32, over the cropped Y,U,V byte stream.
+VP8R_API uint64_t vp8r_checksum_i420(const uint8_t *i420, int width, int height) {
+  if (!i420 || width <= 0 || height <= 0) return 0;
+  const size_t cw = size_t(width + 1) / 2, ch = size_t(height + 1) / 2;
+  const size_t total = size_t(width) * height + 2 * cw * ch;
+  uint32_t s1 = 0, s2 = 0;
+  for (size_t i = 0; i < total; ++i) {
+    s1 += i420[i];
+    s2 += uint32_t(i + 1) * i420[i];
+  }
+  return (uint64_t(s2) << 32) | s1;
+}
+
+}  // extern "C"

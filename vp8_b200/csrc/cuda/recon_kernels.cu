@@ -1,0 +1,861 @@
+// Hand-written sm_100a kernels of the VP8 reconstruction path.
+//
+//   K_inter  : one warp per inter macroblock.  Lanes 0..23 own one 4x4 block each (16 Y, 4 U, 4 V),
+//              lane 24 owns the Y2 block.  Everything from coefficient load to the final store is
+//              lane-local (registers only): dequant -> IWHT/IDCT -> 9x9 reference window ->
+//              horizontal then vertical 6-tap/bilinear pass on packed bytes with dp4a -> residual
+//              add -> store.   Replaces src/inter_predict.cc:246-333, src/residual.cc:42-157,
+//              src/dct.cc:67-133, src/quantizer.cc:10-13 of the reference.
+//   K_intra  : one CTA per frame, one warp per macroblock row, rows advance as a wavefront
+//              (row r may process column c once row r-1 has finished column c+1).  Replaces
+//              src/intra_predict.cc:6-428.
+//   K_filter : same wavefront shape; lanes = the 16+8+8 pixel lines of a macroblock.  Replaces
+//              src/filter.cc:7-340.  Ends with the border extension motion compensation relies on.
+//
+// All arithmetic is integer and bit-exact with the reference, including its int16 wrap-arounds.
+#include "recon_kernels.h"
+
+#include <cstring>
+
+namespace vp8r {
+
+// ------------------------------------------------------------------------------------------
+// constant tables
+// ------------------------------------------------------------------------------------------
+// Sub-pixel filter taps packed as signed bytes: [bilinear][frac][0] = taps 0..3, [..][1] = taps 4,5.
+// frac 0 (identity, tap 128) is special-cased and never looked up.
+__constant__ int c_taps[2][8][2];
+// B_PRED gather table: [mode][pixel] -> i0 | i1<<4 | i2<<8 | kind<<12 over the 13-entry edge
+// array E = {L3,L2,L1,L0,P,A0..A7}.  kind 0: (E[i0]+2E[i1]+E[i2]+2)>>2, 1: (E[i0]+E[i2]+1)>>1,
+// 2: DC, 3: TM = clamp(E[i0]+E[i1]-E[i2]).
+__constant__ unsigned short c_bpred_lut[10 * 16];
+
+static int PackTaps(int a, int b, int c, int d) {
+  return (a & 0xff) | ((b & 0xff) << 8) | ((c & 0xff) << 16) | ((d & 0xff) << 24);
+}
+
+static void BuildBpredLut(unsigned short *lut) {
+  auto L = [](int k) { return 3 - k; };
+  auto A = [](int k) { return 5 + k; };
+  const int P = 4;
+  auto put3 = [&](int mode, int y, int x, int a, int b, int c) {
+    lut[mode * 16 + y * 4 + x] = (unsigned short)(a | (b << 4) | (c << 8) | (0 << 12));
+  };
+  auto put2 = [&](int mode, int y, int x, int a, int c) {
+    lut[mode * 16 + y * 4 + x] = (unsigned short)(a | (a << 4) | (c << 8) | (1 << 12));
+  };
+  for (int y = 0; y < 4; ++y)
+    for (int x = 0; x < 4; ++x) {
+      lut[0 * 16 + y * 4 + x] = (unsigned short)(2 << 12);                                   // B_DC
+      lut[1 * 16 + y * 4 + x] = (unsigned short)(L(y) | (A(x) << 4) | (P << 8) | (3 << 12)); // B_TM
+      put3(2, y, x, 4 + x, 5 + x, 6 + x);                                                    // B_VE
+      put3(3, y, x, 4 - y, 3 - y, (2 - y) > 0 ? 2 - y : 0);                                  // B_HE
+      int d = x + y;
+      put3(4, y, x, 5 + d, 6 + d, (7 + d) < 12 ? 7 + d : 12);                                // B_LD
+      int k = 3 - y + x;
+      put3(5, y, x, k, k + 1, k + 2);                                                        // B_RD
+    }
+  // B_VR (E = first nine entries of the edge array)
+  put3(6, 3, 0, 1, 2, 3); put3(6, 2, 0, 2, 3, 4); put3(6, 3, 1, 3, 4, 5); put3(6, 1, 0, 3, 4, 5);
+  put2(6, 2, 1, 4, 5);    put2(6, 0, 0, 4, 5);    put3(6, 3, 2, 4, 5, 6); put3(6, 1, 1, 4, 5, 6);
+  put2(6, 2, 2, 5, 6);    put2(6, 0, 1, 5, 6);    put3(6, 3, 3, 5, 6, 7); put3(6, 1, 2, 5, 6, 7);
+  put2(6, 2, 3, 6, 7);    put2(6, 0, 2, 6, 7);    put3(6, 1, 3, 6, 7, 8); put2(6, 0, 3, 7, 8);
+  // B_VL
+  put2(7, 0, 0, A(0), A(1));       put3(7, 1, 0, A(0), A(1), A(2)); put2(7, 2, 0, A(1), A(2));
+  put2(7, 0, 1, A(1), A(2));       put3(7, 1, 1, A(1), A(2), A(3)); put3(7, 3, 0, A(1), A(2), A(3));
+  put2(7, 2, 1, A(2), A(3));       put2(7, 0, 2, A(2), A(3));       put3(7, 3, 1, A(2), A(3), A(4));
+  put3(7, 1, 2, A(2), A(3), A(4)); put2(7, 2, 2, A(3), A(4));       put2(7, 0, 3, A(3), A(4));
+  put3(7, 3, 2, A(3), A(4), A(5)); put3(7, 1, 3, A(3), A(4), A(5)); put3(7, 2, 3, A(4), A(5), A(6));
+  put3(7, 3, 3, A(5), A(6), A(7));
+  // B_HD
+  put2(8, 3, 0, 0, 1);    put3(8, 3, 1, 0, 1, 2); put2(8, 2, 0, 1, 2);    put2(8, 3, 2, 1, 2);
+  put3(8, 2, 1, 1, 2, 3); put3(8, 3, 3, 1, 2, 3); put2(8, 2, 2, 2, 3);    put2(8, 1, 0, 2, 3);
+  put3(8, 2, 3, 2, 3, 4); put3(8, 1, 1, 2, 3, 4); put2(8, 1, 2, 3, 4);    put2(8, 0, 0, 3, 4);
+  put3(8, 1, 3, 3, 4, 5); put3(8, 0, 1, 3, 4, 5); put3(8, 0, 2, 4, 5, 6); put3(8, 0, 3, 5, 6, 7);
+  // B_HU
+  put2(9, 0, 0, L(0), L(1));       put3(9, 0, 1, L(0), L(1), L(2)); put2(9, 0, 2, L(1), L(2));
+  put2(9, 1, 0, L(1), L(2));       put3(9, 0, 3, L(1), L(2), L(3)); put3(9, 1, 1, L(1), L(2), L(3));
+  put2(9, 1, 2, L(2), L(3));       put2(9, 2, 0, L(2), L(3));       put3(9, 1, 3, L(2), L(3), L(3));
+  put3(9, 2, 1, L(2), L(3), L(3));
+  put3(9, 2, 2, L(3), L(3), L(3)); put3(9, 2, 3, L(3), L(3), L(3)); put3(9, 3, 0, L(3), L(3), L(3));
+  put3(9, 3, 1, L(3), L(3), L(3)); put3(9, 3, 2, L(3), L(3), L(3)); put3(9, 3, 3, L(3), L(3), L(3));
+}
+
+cudaError_t InitKernelTables() {
+  // src/inter_predict.h:18-36 (RFC 6386 section 18.3)
+  static const int six[8][6] = {{0, 0, 128, 0, 0, 0},  {0, -6, 123, 12, -1, 0},   {2, -11, 108, 36, -8, 1},
+                                {0, -9, 93, 50, -6, 0}, {3, -16, 77, 77, -16, 3}, {0, -6, 50, 93, -9, 0},
+                                {1, -8, 36, 108, -11, 2}, {0, -1, 12, 123, -6, 0}};
+  int taps[2][8][2];
+  for (int f = 0; f < 8; ++f) {
+    taps[0][f][0] = PackTaps(six[f][0], six[f][1], six[f][2], six[f][3]);
+    taps[0][f][1] = PackTaps(six[f][4], six[f][5], 0, 0);
+    taps[1][f][0] = PackTaps(0, 0, 128 - 16 * f, 16 * f);
+    taps[1][f][1] = 0;
+  }
+  cudaError_t err = cudaMemcpyToSymbol(c_taps, taps, sizeof(taps));
+  if (err != cudaSuccess) return err;
+  unsigned short lut[160];
+  std::memset(lut, 0, sizeof(lut));
+  BuildBpredLut(lut);
+  return cudaMemcpyToSymbol(c_bpred_lut, lut, sizeof(lut));
+}
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int clamp255(int x) { return min(max(x, 0), 255); }
+__device__ __forceinline__ int clamp128(int x) { return min(max(x, -128), 127); }
+__device__ __forceinline__ int s16(int x) { return (int)(short)x; }
+
+// src/dct.cc:67-107.  Vertical pass first; values are truncated to int16 between the passes.
+__device__ __forceinline__ void Idct4x4(int *m) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int a = m[i] + m[8 + i], b = m[i] - m[8 + i];
+    int t1 = (m[4 + i] * 35468) >> 16;
+    int t2 = m[12 + i] + ((m[12 + i] * 20091) >> 16);
+    int c = t1 - t2;
+    t1 = m[4 + i] + ((m[4 + i] * 20091) >> 16);
+    t2 = (m[12 + i] * 35468) >> 16;
+    int d = t1 + t2;
+    m[i] = s16(a + d);
+    m[12 + i] = s16(a - d);
+    m[4 + i] = s16(b + c);
+    m[8 + i] = s16(b - c);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int *r = m + 4 * i;
+    int a = r[0] + r[2], b = r[0] - r[2];
+    int t1 = (r[1] * 35468) >> 16;
+    int t2 = r[3] + ((r[3] * 20091) >> 16);
+    int c = t1 - t2;
+    t1 = r[1] + ((r[1] * 20091) >> 16);
+    t2 = (r[3] * 35468) >> 16;
+    int d = t1 + t2;
+    r[0] = s16((a + d + 4) >> 3);
+    r[3] = s16((a - d + 4) >> 3);
+    r[1] = s16((b + c + 4) >> 3);
+    r[2] = s16((b - c + 4) >> 3);
+  }
+}
+
+// src/dct.cc:109-133
+__device__ __forceinline__ void Iwht4x4(int *m) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int a = m[i] + m[12 + i], b = m[4 + i] + m[8 + i];
+    int c = m[4 + i] - m[8 + i], d = m[i] - m[12 + i];
+    m[i] = s16(a + b);
+    m[4 + i] = s16(c + d);
+    m[8 + i] = s16(a - b);
+    m[12 + i] = s16(d - c);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int *r = m + 4 * i;
+    int a = r[0] + r[3], b = r[1] + r[2];
+    int c = r[1] - r[2], d = r[0] - r[3];
+    r[0] = s16((a + b + 3) >> 3);
+    r[1] = s16((c + d + 3) >> 3);
+    r[2] = s16((a - b + 3) >> 3);
+    r[3] = s16((d - c + 3) >> 3);
+  }
+}
+
+// Residual of the macroblock, distributed over the warp: on return lanes 0..23 hold the 4x4
+// residual of "their" block (0..15 Y raster, 16..19 U, 20..23 V) in res[16]; the return value
+// says whether that block has any residual at all.  `y2_slot` is 16 shorts of shared memory
+// private to the warp.  src/residual.cc:42-120, src/quantizer.cc:10-13.
+__device__ __forceinline__ bool WarpResidual(const DevFrameJob &job, const vp8r_mb_info &mb, int lane,
+                                            short *y2_slot, int *res) {
+  const unsigned mask = mb.coef_mask;
+  const bool has_y2 = (mb.flags & VP8R_MB_HAS_Y2) != 0;
+  const int blk = lane < 24 ? lane + 1 : 0;  // index in coef_mask numbering (lane 24: Y2)
+  const bool coded = lane <= 24 && ((mask >> blk) & 1);
+  const int16_t *dq = job.dq[(mb.flags >> VP8R_MB_QSEG_SHIFT) & 3];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) res[i] = 0;
+  if (coded) {
+    const int at = __popc(mask & ((1u << blk) - 1));
+    const int4 *src = reinterpret_cast<const int4 *>(job.payload + (size_t)(mb.coef_offset + at) * 16);
+    int4 lo = __ldg(src), hi = __ldg(src + 1);
+    int w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    int dc = blk == 0 ? dq[VP8R_DQ_Y2_DC] : (blk <= 16 ? dq[VP8R_DQ_Y1_DC] : dq[VP8R_DQ_UV_DC]);
+    int ac = blk == 0 ? dq[VP8R_DQ_Y2_AC] : (blk <= 16 ? dq[VP8R_DQ_Y1_AC] : dq[VP8R_DQ_UV_AC]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      res[2 * i] = s16(s16(w[i]) * ac);        // int16 wrap-around as in the reference
+      res[2 * i + 1] = s16((w[i] >> 16) * ac);
+    }
+    res[0] = s16(s16(w[0]) * dc);
+  }
+  bool any = coded;
+  if (has_y2 && (mask & 1)) {  // warp-uniform
+    if (lane == 24) {
+      Iwht4x4(res);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) y2_slot[i] = (short)res[i];
+    }
+    __syncwarp();
+    if (lane < 16) {
+      res[0] = y2_slot[lane];
+      any = true;
+    }
+    __syncwarp();
+  }
+  if (lane < 24 && any) Idct4x4(res);
+  return lane < 24 && any;
+}
+
+// ------------------------------------------------------------------------------------------
+// K_inter
+// ------------------------------------------------------------------------------------------
+// Horizontal (or, on the transposed block, vertical) filter of 4 outputs from 9 packed bytes:
+// `lo` = bytes 0..3, `mid` = bytes 4..7, `hi` = byte 8 (upper bytes ignored).
+__device__ __forceinline__ unsigned Filter4(unsigned lo, unsigned mid, unsigned hi, int t03, int t45) {
+  unsigned out = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    unsigned a = j ? __funnelshift_r(lo, mid, 8 * j) : lo;
+    unsigned b = j ? __funnelshift_r(mid, hi, 8 * j) : mid;
+    int s = dp4a_us(a, t03, 64);
+    s = dp4a_us(b, t45, s);
+    out |= (unsigned)clamp255(s >> 7) << (8 * j);
+  }
+  return out;
+}
+
+__device__ __forceinline__ void Transpose4x4(unsigned r0, unsigned r1, unsigned r2, unsigned r3, unsigned &c0,
+                                             unsigned &c1, unsigned &c2, unsigned &c3) {
+  unsigned t0 = __byte_perm(r0, r1, 0x5140), t1 = __byte_perm(r2, r3, 0x5140);
+  unsigned t2 = __byte_perm(r0, r1, 0x7362), t3 = __byte_perm(r2, r3, 0x7362);
+  c0 = __byte_perm(t0, t1, 0x5410);
+  c1 = __byte_perm(t0, t1, 0x7632);
+  c2 = __byte_perm(t2, t3, 0x5410);
+  c3 = __byte_perm(t2, t3, 0x7632);
+}
+
+constexpr int kInterWarps = 4;
+
+__global__ void __launch_bounds__(kInterWarps * 32) InterKernel(const DevFrameJob *__restrict__ jobs) {
+  __shared__ short s_y2[kInterWarps][16];
+  const DevFrameJob &job = jobs[blockIdx.y];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mb_index = blockIdx.x * kInterWarps + warp;
+  if (job.n_inter == 0 || mb_index >= job.mb_cols * job.mb_rows) return;
+  vp8r_mb_info mb;
+  {
+    const int4 *p = reinterpret_cast<const int4 *>(job.mbs + mb_index);
+    int4 a = __ldg(p), b = __ldg(p + 1);
+    mb.flags = a.x; mb.coef_mask = a.y; mb.coef_offset = a.z;
+    mb.mv[0] = (short)(a.w & 0xffff); mb.mv[1] = (short)(a.w >> 16);
+    mb.aux[0] = b.x; mb.aux[1] = b.y;
+  }
+  if (!(mb.flags & VP8R_MB_IS_INTER)) return;
+
+  int res[16];
+  const bool has_res = WarpResidual(job, mb, lane, s_y2[warp], res);
+  if (lane >= 24) return;
+
+  const int mb_r = mb_index / job.mb_cols, mb_c = mb_index - mb_r * job.mb_cols;
+  const bool split = ((mb.flags >> VP8R_MB_MODE_SHIFT) & 7) == 4;
+  const int ref_id = (mb.flags >> VP8R_MB_REF_SHIFT) & 3;
+  const int *split_mv = reinterpret_cast<const int *>(job.payload + (size_t)mb.aux[0] * 16);
+
+  // Block geometry and motion vector (1/8 pel) of this lane.
+  int mvr, mvc, bx, by, pitch, plane_w, plane_h;
+  const uint8_t *ref;
+  uint8_t *dst;
+  if (lane < 16) {
+    int m = split ? __ldg(split_mv + lane) : (int)((unsigned short)mb.mv[0] | ((unsigned)(unsigned short)mb.mv[1] << 16));
+    mvr = (short)(m & 0xffff);
+    mvc = m >> 16;
+    by = mb_r * 16 + (lane >> 2) * 4;
+    bx = mb_c * 16 + (lane & 3) * 4;
+    pitch = job.pitch_y;
+    plane_w = job.mb_cols * 16;
+    plane_h = job.mb_rows * 16;
+    ref = job.ref[ref_id].y;
+    dst = job.cur.y;
+  } else {
+    // Chroma MV: sum of the four luma MVs under the block, rounded away from zero, /8
+    // (src/inter_predict.cc:116-144; the reference discards its own clamp of the result).
+    const int b = lane & 3, i = b >> 1, j = b & 1;
+    int sr, sc;
+    if (split) {
+      const int k0 = i * 8 + j * 2;
+      int m0 = __ldg(split_mv + k0), m1 = __ldg(split_mv + k0 + 1), m2 = __ldg(split_mv + k0 + 4),
+          m3 = __ldg(split_mv + k0 + 5);
+      sr = (short)(m0 & 0xffff) + (short)(m1 & 0xffff) + (short)(m2 & 0xffff) + (short)(m3 & 0xffff);
+      sc = (m0 >> 16) + (m1 >> 16) + (m2 >> 16) + (m3 >> 16);
+    } else {
+      sr = 4 * mb.mv[0];
+      sc = 4 * mb.mv[1];
+    }
+    sr = s16(sr);
+    sc = s16(sc);
+    mvr = (sr >= 0 ? (sr + 4) : (sr - 4)) / 8;
+    mvc = (sc >= 0 ? (sc + 4) : (sc - 4)) / 8;
+    if (job.version == 3) {
+      mvr &= ~7;
+      mvc &= ~7;
+    }
+    by = mb_r * 8 + i * 4;
+    bx = mb_c * 8 + j * 4;
+    pitch = job.pitch_c;
+    plane_w = job.mb_cols * 8;
+    plane_h = job.mb_rows * 8;
+    ref = lane < 20 ? job.ref[ref_id].u : job.ref[ref_id].v;
+    dst = lane < 20 ? job.cur.u : job.cur.v;
+  }
+
+  const int fr = mvr & 7, fc = mvc & 7;
+  // 9x9 window origin, clamped as a whole into the padded plane (see kBorder).
+  int wy = by + (mvr >> 3) - 2, wx = bx + (mvc >> 3) - 2;
+  wy = min(max(wy, -kBorder), plane_h + kBorder - 9);
+  wx = min(max(wx, -kBorder), plane_w + kBorder - 9);
+  const uint8_t *wp = ref + (ptrdiff_t)wy * pitch + wx;
+  const unsigned shift = ((unsigned)(size_t)wp & 3u) * 8;
+  const unsigned *wrow = reinterpret_cast<const unsigned *>(wp - ((size_t)wp & 3));
+  const int wpitch = pitch >> 2;
+
+  unsigned out[4];  // predicted rows, 4 packed pixels each
+  if ((fr | fc) == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const unsigned *p = wrow + (i + 2) * wpitch;
+      unsigned w0 = p[0], w1 = p[1], w2 = p[2];
+      unsigned lo = __funnelshift_r(w0, w1, shift), mid = __funnelshift_r(w1, w2, shift);
+      out[i] = __funnelshift_r(lo, mid, 16);
+    }
+  } else {
+    const int bil = job.version != 0;
+    unsigned h[9];
+    if (fc) {
+      const int t03 = c_taps[bil][fc][0], t45 = c_taps[bil][fc][1];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const unsigned *p = wrow + i * wpitch;
+        unsigned w0 = p[0], w1 = p[1], w2 = p[2];
+        unsigned lo = __funnelshift_r(w0, w1, shift), mid = __funnelshift_r(w1, w2, shift), hi = w2 >> shift;
+        h[i] = Filter4(lo, mid, hi, t03, t45);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const unsigned *p = wrow + i * wpitch;
+        unsigned w0 = p[0], w1 = p[1], w2 = p[2];
+        unsigned lo = __funnelshift_r(w0, w1, shift), mid = __funnelshift_r(w1, w2, shift);
+        h[i] = __funnelshift_r(lo, mid, 16);
+      }
+    }
+    if (fr) {
+      const int t03 = c_taps[bil][fr][0], t45 = c_taps[bil][fr][1];
+      unsigned a0, a1, a2, a3, b0, b1, b2, b3;
+      Transpose4x4(h[0], h[1], h[2], h[3], a0, a1, a2, a3);
+      Transpose4x4(h[4], h[5], h[6], h[7], b0, b1, b2, b3);
+      unsigned c0 = Filter4(a0, b0, h[8], t03, t45);
+      unsigned c1 = Filter4(a1, b1, h[8] >> 8, t03, t45);
+      unsigned c2 = Filter4(a2, b2, h[8] >> 16, t03, t45);
+      unsigned c3 = Filter4(a3, b3, h[8] >> 24, t03, t45);
+      Transpose4x4(c0, c1, c2, c3, out[0], out[1], out[2], out[3]);
+    } else {
+      out[0] = h[2]; out[1] = h[3]; out[2] = h[4]; out[3] = h[5];
+    }
+  }
+
+  uint8_t *d = dst + (ptrdiff_t)by * pitch + bx;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    unsigned v = out[i];
+    if (has_res) {  // src/residual.cc:139-149: clamp255(int16(pred + res))
+      unsigned o = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o |= (unsigned)clamp255(s16((int)((v >> (8 * j)) & 0xff) + res[i * 4 + j])) << (8 * j);
+      v = o;
+    }
+    *reinterpret_cast<unsigned *>(d + (ptrdiff_t)i * pitch) = v;
+  }
+}
+
+cudaError_t LaunchInter(const DevFrameJob *jobs, int n_frames, int max_mbs, cudaStream_t st) {
+  dim3 grid((max_mbs + kInterWarps - 1) / kInterWarps, n_frames);
+  InterKernel<<<grid, kInterWarps * 32, 0, st>>>(jobs);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// wavefront plumbing shared by K_intra and K_filter
+// ------------------------------------------------------------------------------------------
+constexpr int kWaveWarps = 32;
+
+__device__ __forceinline__ void WaitRow(volatile int *progress, int row, int need) {
+  if (row < 0) return;
+  while (progress[row] < need) __nanosleep(40);
+  __threadfence_block();
+}
+__device__ __forceinline__ void PublishRow(volatile int *progress, int row, int done, int lane) {
+  __syncwarp();
+  __threadfence_block();
+  if (lane == 0) progress[row] = done;
+}
+
+// ------------------------------------------------------------------------------------------
+// K_intra
+// ------------------------------------------------------------------------------------------
+struct IntraScratch {
+  short y2[16];
+  short res[24][16];
+  unsigned char tile[17][24];  // B_PRED working tile: row 0 = row above, column 3 = column left,
+                               // macroblock pixel (y,x) at tile[1+y][4+x]; columns 20..23 of row 0
+                               // hold the above-right pixels.
+};
+
+// 16x16 / 8x8 prediction of one 4x4 block by its owning lane (src/intra_predict.cc:6-98).
+// Every lane of the warp must call this (it shuffles); only lanes < 24 produce output.
+__device__ __forceinline__ void PredictMbBlock(const DevFrameJob &job, int mb_r, int mb_c, int lane, int ymode,
+                                               int uvmode, bool do_luma, const short *res, bool has_res) {
+  const bool luma = lane < 16;
+  const int n4 = luma ? 4 : 2;
+  const int first = luma ? 0 : (lane < 20 ? 16 : 20);
+  const int b = lane - first, i = luma ? (b >> 2) : (b >> 1), j = luma ? (b & 3) : (b & 1);
+  const int pitch = luma ? job.pitch_y : job.pitch_c;
+  uint8_t *plane = luma ? job.cur.y : (lane < 20 ? job.cur.u : job.cur.v);
+  const int n = luma ? 16 : 8;
+  uint8_t *mbp = plane + (ptrdiff_t)(mb_r * n) * pitch + mb_c * n;
+  const bool active = lane < 24 && (do_luma || !luma);
+  const int mode = luma ? ymode : uvmode;
+  const bool have_above = mb_r > 0, have_left = mb_c > 0;
+
+  unsigned aw = 0x7f7f7f7fu;
+  int l[4] = {129, 129, 129, 129};
+  int P = have_above ? (have_left ? 0 : 129) : 127;
+  if (lane < 24) {
+    if (have_above) aw = *reinterpret_cast<const unsigned *>(mbp - pitch + 4 * j);
+    if (have_left) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) l[k] = mbp[(ptrdiff_t)(4 * i + k) * pitch - 1];
+    }
+    if (have_above && have_left) P = mbp[-pitch - 1];
+  }
+  // DC needs the sums over the whole edge: gather from the lanes on the first block row / column.
+  int sum_a = (int)__dp4a(aw, 0x01010101u, 0u);
+  int sum_l = l[0] + l[1] + l[2] + l[3];
+  int tot_a = 0, tot_l = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int va = __shfl_sync(0xffffffffu, sum_a, first + (k < n4 ? k : 0));
+    int vl = __shfl_sync(0xffffffffu, sum_l, first + (k < n4 ? k * n4 : 0));
+    if (k < n4) {
+      tot_a += va;
+      tot_l += vl;
+    }
+  }
+  if (!active) return;
+
+  unsigned rows[4];
+  if (mode == 1) {  // V_PRED
+    rows[0] = rows[1] = rows[2] = rows[3] = aw;
+  } else if (mode == 2) {  // H_PRED
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rows[k] = (unsigned)l[k] * 0x01010101u;
+  } else if (mode == 0) {  // DC_PRED
+    int v = 128;
+    if (have_above || have_left) {
+      int shf = (luma ? 3 : 2) + (have_above ? 1 : 0) + (have_left ? 1 : 0);
+      int sum = (have_above ? tot_a : 0) + (have_left ? tot_l : 0);
+      v = (sum + (1 << (shf - 1))) >> shf;
+    }
+    rows[0] = rows[1] = rows[2] = rows[3] = (unsigned)v * 0x01010101u;
+  } else {  // TM_PRED
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      unsigned o = 0;
+#pragma unroll
+      for (int x = 0; x < 4; ++x) o |= (unsigned)clamp255(l[k] + (int)((aw >> (8 * x)) & 0xff) - P) << (8 * x);
+      rows[k] = o;
+    }
+  }
+  uint8_t *d = mbp + (ptrdiff_t)(4 * i) * pitch + 4 * j;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    unsigned v = rows[k];
+    if (has_res) {
+      unsigned o = 0;
+#pragma unroll
+      for (int x = 0; x < 4; ++x) o |= (unsigned)clamp255(s16((int)((v >> (8 * x)) & 0xff) + res[k * 4 + x])) << (8 * x);
+      v = o;
+    }
+    *reinterpret_cast<unsigned *>(d + (ptrdiff_t)k * pitch) = v;
+  }
+}
+
+// B_PRED luma of one macroblock by one warp (src/intra_predict.cc:100-351).
+__device__ __forceinline__ void PredictBpred(const DevFrameJob &job, int mb_r, int mb_c, int lane,
+                                             const vp8r_mb_info &mb, IntraScratch &s, unsigned res_mask,
+                                             const unsigned short *lut) {
+  const int pitch = job.pitch_y;
+  uint8_t *mbp = job.cur.y + (ptrdiff_t)(mb_r * 16) * pitch + mb_c * 16;
+  // Row above: columns -1..19 -> tile[0][3..23].
+  if (lane < 21) {
+    int col = lane - 1, v;
+    if (mb_r == 0) {
+      v = 127;
+    } else if (col < 0) {
+      v = mb_c == 0 ? 129 : mbp[-pitch - 1];
+    } else if (col >= 16 && mb_c + 1 == job.mb_cols) {
+      v = mbp[-pitch + 15];  // src/intra_predict.cc:130-132
+    } else {
+      v = mbp[-pitch + col];
+    }
+    s.tile[0][4 + col] = (unsigned char)v;
+  }
+  if (lane < 16) s.tile[1 + lane][3] = (unsigned char)(mb_c == 0 ? 129 : mbp[(ptrdiff_t)lane * pitch - 1]);
+  __syncwarp();
+
+  const int py = (lane >> 2) & 3, px = lane & 3;
+  for (int b = 0; b < 16; ++b) {
+    const int i = b >> 2, j = b & 3;
+    const int mode = (int)((mb.aux[b >> 3] >> ((b & 7) * 4)) & 15);
+    // Edge array E[0..12] = L3,L2,L1,L0,P,A0..A7, one entry per lane.
+    int E = 0;
+    if (lane < 4) {
+      E = s.tile[1 + 4 * i + (3 - lane)][3 + 4 * j];
+    } else if (lane < 9) {
+      E = s.tile[4 * i][3 + 4 * j + (lane - 4)];
+    } else if (lane < 13) {
+      const int row = (j == 3) ? 0 : 4 * i;  // right-most column: always the macroblock row above
+      E = s.tile[row][3 + 4 * j + (lane - 4)];
+    }
+    const unsigned e = lut[mode * 16 + (lane & 15)];
+    const int x0 = __shfl_sync(0xffffffffu, E, e & 15);
+    const int x1 = __shfl_sync(0xffffffffu, E, (e >> 4) & 15);
+    const int x2 = __shfl_sync(0xffffffffu, E, (e >> 8) & 15);
+    const int dc_in = (lane < 4 || (lane >= 5 && lane < 9)) ? E : 0;
+    const int dc = (__reduce_add_sync(0xffffffffu, dc_in) + 4) >> 3;
+    const int kind = e >> 12;
+    int v;
+    if (kind == 0) v = (x0 + 2 * x1 + x2 + 2) >> 2;
+    else if (kind == 1) v = (x0 + x2 + 1) >> 1;
+    else if (kind == 2) v = dc;
+    else v = clamp255(x0 + x1 - x2);
+    if (lane < 16) {
+      if ((res_mask >> b) & 1) v = clamp255(s16(v + s.res[b][lane]));
+      s.tile[1 + 4 * i + py][4 + 4 * j + px] = (unsigned char)v;
+    }
+    __syncwarp();
+  }
+  if (lane < 16) {
+    const unsigned *t = reinterpret_cast<const unsigned *>(&s.tile[1 + lane][4]);
+    uint4 v = make_uint4(t[0], t[1], t[2], t[3]);
+    *reinterpret_cast<uint4 *>(mbp + (ptrdiff_t)lane * pitch) = v;
+  }
+}
+
+__global__ void __launch_bounds__(kWaveWarps * 32) IntraKernel(const DevFrameJob *__restrict__ jobs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const DevFrameJob &job = jobs[blockIdx.x];
+  if (job.n_intra == 0) return;
+  const int rows = job.mb_rows, cols = job.mb_cols;
+  volatile int *progress = reinterpret_cast<volatile int *>(smem_raw);
+  unsigned short *lut = reinterpret_cast<unsigned short *>(smem_raw + ((rows * 4 + 15) & ~15));
+  IntraScratch *scratch = reinterpret_cast<IntraScratch *>(reinterpret_cast<unsigned char *>(lut) + 320);
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) progress[i] = 0;
+  for (int i = threadIdx.x; i < 160; i += blockDim.x) lut[i] = c_bpred_lut[i];
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  IntraScratch &s = scratch[warp];
+  for (int r = warp; r < rows; r += kWaveWarps) {
+    for (int c0 = 0; c0 < cols; c0 += 32) {
+      // Which of the next 32 macroblocks of this row are intra coded?
+      unsigned flags = 0;
+      if (c0 + lane < cols) flags = __ldg(&job.mbs[r * cols + c0 + lane].flags);
+      unsigned intra_mask = __ballot_sync(0xffffffffu, (c0 + lane < cols) && !(flags & VP8R_MB_IS_INTER));
+      while (intra_mask) {
+        const int k = __ffs(intra_mask) - 1;
+        intra_mask &= intra_mask - 1;
+        const int c = c0 + k;
+        vp8r_mb_info mb;
+        {
+          const int4 *p = reinterpret_cast<const int4 *>(job.mbs + r * cols + c);
+          int4 a = __ldg(p), b = __ldg(p + 1);
+          mb.flags = a.x; mb.coef_mask = a.y; mb.coef_offset = a.z;
+          mb.aux[0] = b.x; mb.aux[1] = b.y;
+        }
+        int res[16];
+        const bool has_res = WarpResidual(job, mb, lane, s.y2, res);
+        const unsigned res_mask = __ballot_sync(0xffffffffu, has_res);
+        if (lane < 24) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) s.res[lane][i] = (short)res[i];
+        }
+        // Everything above and to the left must be final (unfiltered) pixels of this frame.
+        WaitRow(progress, r - 1, min(c + 2, cols));
+        __syncwarp();
+        const int ymode = (mb.flags >> VP8R_MB_MODE_SHIFT) & 7, uvmode = (mb.flags >> VP8R_MB_UVMODE_SHIFT) & 3;
+        PredictMbBlock(job, r, c, lane, ymode, uvmode, ymode != 4, lane < 24 ? s.res[lane] : s.res[0], has_res);
+        if (ymode == 4) PredictBpred(job, r, c, lane, mb, s, res_mask, lut);
+        PublishRow(progress, r, c + 1, lane);
+      }
+      PublishRow(progress, r, min(c0 + 32, cols), lane);
+    }
+  }
+}
+
+static size_t IntraSmemBytes(int max_rows) {
+  return ((size_t(max_rows) * 4 + 15) & ~size_t(15)) + 320 + sizeof(IntraScratch) * kWaveWarps;
+}
+
+cudaError_t LaunchIntra(const DevFrameJob *jobs, int n_frames, int max_rows, cudaStream_t st) {
+  size_t smem = IntraSmemBytes(max_rows);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(IntraKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  IntraKernel<<<n_frames, kWaveWarps * 32, smem, st>>>(jobs);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K_filter
+// ------------------------------------------------------------------------------------------
+struct LfLimits {
+  int interior, hev, edge_mb, edge_sb;
+};
+
+// src/filter.cc:119-149
+__device__ __forceinline__ LfLimits MakeLimits(int level, int sharp, bool key) {
+  LfLimits l;
+  int in = level;
+  if (sharp) {
+    in >>= (sharp > 4) ? 2 : 1;
+    in = min(in, 9 - sharp);
+  }
+  l.interior = max(in, 1);
+  if (key) l.hev = level >= 40 ? 2 : (level >= 15 ? 1 : 0);
+  else l.hev = level >= 40 ? 3 : (level >= 20 ? 2 : (level >= 15 ? 1 : 0));
+  l.edge_mb = (level + 2) * 2 + l.interior;
+  l.edge_sb = level * 2 + l.interior;
+  return l;
+}
+
+// src/filter.cc:22-35
+__device__ __forceinline__ void LfAdjust(int &p1, int &p0, int &q0, int &q1, bool outer) {
+  int a = clamp128((outer ? clamp128(p1 - q1) : 0) + 3 * (q0 - p0));
+  int f1 = min(a + 4, 127) >> 3, f2 = min(a + 3, 127) >> 3;
+  p0 = clamp255(p0 + f2);
+  q0 = clamp255(q0 - f1);
+  if (!outer) {
+    a = (f1 + 1) >> 1;
+    p1 = clamp255(p1 + a);
+    q1 = clamp255(q1 - a);
+  }
+}
+
+// One edge on 8 pixels v[0..7] = p3 p2 p1 p0 | q0 q1 q2 q3.  kind: 0 macroblock edge, 1 sub-block
+// edge (src/filter.cc:37-67); simple = luma-only simple filter (src/filter.cc:14-16,69-71).
+__device__ __forceinline__ void LfEdge(int *v, const LfLimits &lim, bool mb_edge, bool simple) {
+  const int edge = mb_edge ? lim.edge_mb : lim.edge_sb;
+  int &p3 = v[0], &p2 = v[1], &p1 = v[2], &p0 = v[3], &q0 = v[4], &q1 = v[5], &q2 = v[6], &q3 = v[7];
+  if (abs(p0 - q0) * 2 + (abs(p1 - q1) >> 1) > edge) return;
+  if (simple) {
+    LfAdjust(p1, p0, q0, q1, true);
+    return;
+  }
+  const int I = lim.interior;
+  if (abs(p3 - p2) > I || abs(p2 - p1) > I || abs(p1 - p0) > I || abs(q0 - q1) > I || abs(q1 - q2) > I ||
+      abs(q2 - q3) > I)
+    return;
+  const bool hev = abs(p1 - p0) > lim.hev || abs(q1 - q0) > lim.hev;
+  if (!mb_edge) {
+    LfAdjust(p1, p0, q0, q1, hev);
+  } else if (hev) {
+    LfAdjust(p1, p0, q0, q1, true);
+  } else {
+    int w = clamp128(clamp128(p1 - q1) + 3 * (q0 - p0));
+    int a = (27 * w + 63) >> 7;
+    q0 = clamp255(q0 - a);
+    p0 = clamp255(p0 + a);
+    a = (18 * w + 63) >> 7;
+    q1 = clamp255(q1 - a);
+    p1 = clamp255(p1 + a);
+    a = (9 * w + 63) >> 7;
+    q2 = clamp255(q2 - a);
+    p2 = clamp255(p2 + a);
+  }
+}
+
+// Extends the finished frame by kBorder replicated pixels on every side (8-byte granules: plane
+// widths are multiples of 8).
+__device__ void ExtendBorders(const DevFrameJob &job) {
+  for (int pl = 0; pl < 3; ++pl) {
+    uint8_t *base = pl == 0 ? job.cur.y : (pl == 1 ? job.cur.u : job.cur.v);
+    const int pitch = pl == 0 ? job.pitch_y : job.pitch_c;
+    const int w = job.mb_cols * (pl == 0 ? 16 : 8), h = job.mb_rows * (pl == 0 ? 16 : 8);
+    for (int t = threadIdx.x; t < h * 8; t += blockDim.x) {  // left / right, 8 bytes per item
+      const int row = t >> 3, part = t & 7;
+      uint8_t *rowp = base + (ptrdiff_t)row * pitch;
+      unsigned v = (part < 4 ? rowp[0] : rowp[w - 1]) * 0x01010101u;
+      uint8_t *d = part < 4 ? rowp - kBorder + 8 * part : rowp + w + 8 * (part - 4);
+      *reinterpret_cast<uint2 *>(d) = make_uint2(v, v);
+    }
+  }
+  __syncthreads();
+  for (int pl = 0; pl < 3; ++pl) {
+    uint8_t *base = pl == 0 ? job.cur.y : (pl == 1 ? job.cur.u : job.cur.v);
+    const int pitch = pl == 0 ? job.pitch_y : job.pitch_c;
+    const int w = job.mb_cols * (pl == 0 ? 16 : 8), h = job.mb_rows * (pl == 0 ? 16 : 8);
+    const int vecs = (w + 2 * kBorder) / 8;
+    for (int t = threadIdx.x; t < vecs * 2 * kBorder; t += blockDim.x) {  // top / bottom rows
+      const int k = t / vecs, x = t - k * vecs;
+      const int src_row = k < kBorder ? 0 : h - 1;
+      const int dst_row = k < kBorder ? k - kBorder : h + (k - kBorder);
+      const uint2 v = *reinterpret_cast<const uint2 *>(base + (ptrdiff_t)src_row * pitch - kBorder + 8 * x);
+      *reinterpret_cast<uint2 *>(base + (ptrdiff_t)dst_row * pitch - kBorder + 8 * x) = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kWaveWarps * 32) FilterKernel(const DevFrameJob *__restrict__ jobs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const DevFrameJob &job = jobs[blockIdx.x];
+  const int rows = job.mb_rows, cols = job.mb_cols;
+  volatile int *progress = reinterpret_cast<volatile int *>(smem_raw);
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) progress[i] = 0;
+  __syncthreads();
+
+  if (job.lf_level != 0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool simple = job.filter_type != 0;
+    const bool luma = lane < 16;
+    const int n = luma ? 16 : 8;
+    const int line = luma ? lane : (lane & 7);  // pixel row (vertical edges) / column (horizontal)
+    uint8_t *plane = luma ? job.cur.y : (lane < 24 ? job.cur.u : job.cur.v);
+    const int pitch = luma ? job.pitch_y : job.pitch_c;
+    const bool lane_on = luma || !simple;
+    const int n_edges = n / 4;
+
+    for (int r = warp; r < rows; r += kWaveWarps) {
+      for (int c = 0; c < cols; ++c) {
+        const unsigned flags = __ldg(&job.mbs[r * cols + c].flags);
+        const int level = (flags >> VP8R_MB_LF_SHIFT) & 63;
+        if (level) {
+          const bool inner = (flags & VP8R_MB_LF_INNER) != 0;
+          const LfLimits lim = MakeLimits(level, job.sharpness, job.key_frame != 0);
+          WaitRow(progress, r - 1, min(c + 2, cols));
+          uint8_t *mbp = plane + (ptrdiff_t)(r * n) * pitch + c * n;
+          if (lane_on) {
+            // ---- vertical edges: this lane owns pixel row `line`, columns -4 .. n-1 ----
+            unsigned *rowp = reinterpret_cast<unsigned *>(mbp + (ptrdiff_t)line * pitch - 4);
+            int v[20];
+#pragma unroll
+            for (int wd = 0; wd < 5; ++wd) {
+              if (wd <= n_edges) {
+                unsigned x = rowp[wd];
+                v[4 * wd] = x & 0xff; v[4 * wd + 1] = (x >> 8) & 0xff;
+                v[4 * wd + 2] = (x >> 16) & 0xff; v[4 * wd + 3] = x >> 24;
+              }
+            }
+            if (c > 0) LfEdge(v, lim, true, simple);
+            if (inner) {
+#pragma unroll
+              for (int e = 1; e < 4; ++e)
+                if (e < n_edges) LfEdge(v + 4 * e, lim, false, simple);
+            }
+#pragma unroll
+            for (int wd = 0; wd < 5; ++wd) {
+              if (wd <= n_edges && (wd > 0 || c > 0))
+                rowp[wd] = (unsigned)v[4 * wd] | ((unsigned)v[4 * wd + 1] << 8) | ((unsigned)v[4 * wd + 2] << 16) |
+                           ((unsigned)v[4 * wd + 3] << 24);
+            }
+          }
+          __syncwarp();
+          if (lane_on) {
+            // ---- horizontal edges: this lane owns pixel column `line`, rows -4 .. n-1 ----
+            uint8_t *colp = mbp + line;
+            int v[20];
+#pragma unroll
+            for (int y = 0; y < 20; ++y)
+              if (y < n + 4 && (y >= 4 || r > 0)) v[y] = colp[(ptrdiff_t)(y - 4) * pitch];
+            if (r > 0) LfEdge(v, lim, true, simple);
+            if (inner) {
+#pragma unroll
+              for (int e = 1; e < 4; ++e)
+                if (e < n_edges) LfEdge(v + 4 * e, lim, false, simple);
+            }
+#pragma unroll
+            for (int y = 1; y < 19; ++y)
+              if (y < n + 3 && (y >= 4 || r > 0)) colp[(ptrdiff_t)(y - 4) * pitch] = (uint8_t)v[y];
+          }
+        }
+        PublishRow(progress, r, c + 1, lane);
+      }
+    }
+  }
+  __syncthreads();
+  ExtendBorders(job);
+}
+
+cudaError_t LaunchFilter(const DevFrameJob *jobs, int n_frames, int max_rows, cudaStream_t st) {
+  size_t smem = (size_t(max_rows) * 4 + 15) & ~size_t(15);
+  FilterKernel<<<n_frames, kWaveWarps * 32, smem, st>>>(jobs);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// checksum of the cropped I420 image: s1 = sum(b_i), s2 = sum((i+1) * b_i), both mod 2^32,
+// with i the byte index in the cropped Y,U,V stream (src/yuv.cc:6-28 order).
+// ------------------------------------------------------------------------------------------
+__global__ void ChecksumKernel(const DevFrameJob *__restrict__ jobs) {
+  const DevFrameJob &job = jobs[blockIdx.y];
+  if (!job.checksum) return;
+  const int w = job.width, h = job.height, cw = (w + 1) / 2, ch = (h + 1) / 2;
+  const unsigned ny = (unsigned)w * h, nc = (unsigned)cw * ch, total = ny + 2 * nc;
+  unsigned s1 = 0, s2 = 0;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned b;
+    if (i < ny) {
+      unsigned y = i / w, x = i - y * w;
+      b = job.cur.y[(size_t)y * job.pitch_y + x];
+    } else {
+      unsigned k = i - ny;
+      const uint8_t *pl = job.cur.u;
+      if (k >= nc) {
+        k -= nc;
+        pl = job.cur.v;
+      }
+      unsigned y = k / cw, x = k - y * cw;
+      b = pl[(size_t)y * job.pitch_c + x];
+    }
+    s1 += b;
+    s2 += (i + 1) * b;
+  }
+  for (int o = 16; o; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    // low and high words are accumulated independently (mod 2^32 each) with two 32-bit atomics
+    unsigned *out = reinterpret_cast<unsigned *>(job.checksum);
+    atomicAdd(out, s1);
+    atomicAdd(out + 1, s2);
+  }
+}
+
+cudaError_t LaunchChecksum(const DevFrameJob *jobs, int n_frames, cudaStream_t st) {
+  dim3 grid(64, n_frames);
+  ChecksumKernel<<<grid, 256, 0, st>>>(jobs);
+  return cudaGetLastError();
+}
+
+}  // namespace vp8r

@@ -1,0 +1,52 @@
+// Device-side job description and launch entry points of the reconstruction kernels.
+#ifndef VP8R_CUDA_RECON_KERNELS_H_
+#define VP8R_CUDA_RECON_KERNELS_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vp8r.h"
+
+namespace vp8r {
+
+// Replicated border (pixels) around every plane of a surface.  Motion-compensation windows are
+// clamped as a whole into the padded plane, which is bit-identical to the reference's per-pixel
+// coordinate clamp (src/inter_predict.cc:252-256) once the border is >= the window size.
+constexpr int kBorder = 32;
+
+struct DevPlanes {
+  uint8_t *y, *u, *v;  // address of pixel (0,0) of each plane
+};
+
+// One frame of one stream inside a batched launch.
+struct DevFrameJob {
+  const vp8r_mb_info *mbs;
+  const int16_t *payload;
+  DevPlanes cur;
+  DevPlanes ref[4];  // indexed by reference frame id 1..3 (last, golden, altref)
+  int pitch_y, pitch_c;
+  int mb_cols, mb_rows;
+  int n_intra, n_inter;
+  int16_t dq[4][6];
+  uint8_t key_frame, version, filter_type, lf_level, sharpness;
+  uint8_t pad[3];
+  // output side (crop / checksum)
+  int width, height;
+  unsigned long long *checksum;  // optional: receives the I420 checksum
+};
+
+// Uploads the constant tables (filter taps, B_PRED gather LUT).  Once per device.
+cudaError_t InitKernelTables();
+
+// K_inter: dequant + IWHT/IDCT + motion compensation + residual add for every inter MB.
+cudaError_t LaunchInter(const DevFrameJob *jobs, int n_frames, int max_mbs, cudaStream_t st);
+// K_intra: dequant + IWHT/IDCT + intra prediction as a per-frame macroblock wavefront.
+cudaError_t LaunchIntra(const DevFrameJob *jobs, int n_frames, int max_rows, cudaStream_t st);
+// K_filter: normal/simple loop filter as a per-frame macroblock wavefront, then border extension.
+cudaError_t LaunchFilter(const DevFrameJob *jobs, int n_frames, int max_rows, cudaStream_t st);
+// Device-side checksum of the cropped I420 image of each job's current surface.
+cudaError_t LaunchChecksum(const DevFrameJob *jobs, int n_frames, cudaStream_t st);
+
+}  // namespace vp8r
+
+#endif  // VP8R_CUDA_RECON_KERNELS_H_

@@ -1,0 +1,628 @@
+// Runtime around the kernels: engine (device, CUDA stream, staging), stream contexts (surface
+// pool + last/golden/altref bookkeeping, the role of ref_frames[] in src/decode.cc:40 and
+// RefreshRefFrames in src/loop.h:19-46), batched submission, read-back, timers, C ABI.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../cuda/recon_kernels.h"
+#include "../host/frame_parser.h"
+#include "../host/parsed_frame.h"
+#include "error.h"
+#include "vp8r.h"
+
+namespace vp8r {
+
+// ------------------------------------------------------------------ host / device memory ----
+void *HostAlloc(size_t bytes, bool pinned) {
+  if (!pinned) return std::malloc(bytes);
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void HostFree(void *p, bool pinned) {
+  if (!p) return;
+  if (pinned) cudaFreeHost(p);
+  else std::free(p);
+}
+void DeviceFree(void *p, int device) {
+  if (!p) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (device >= 0 && device != prev) cudaSetDevice(device);
+  cudaFree(p);
+  if (device >= 0 && device != prev && prev >= 0) cudaSetDevice(prev);
+}
+
+#define CU_TRY(expr)                                                                         \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      SetError(std::string(#expr) + ": " + cudaGetErrorString(_e));                          \
+      return VP8R_ERR_CUDA;                                                                  \
+    }                                                                                        \
+  } while (0)
+
+struct Surface {
+  uint8_t *base = nullptr;
+  DevPlanes planes{};
+};
+
+}  // namespace vp8r
+
+using vp8r::DevFrameJob;
+using vp8r::SetError;
+
+struct vp8r_stream {
+  vp8r_engine *eng = nullptr;
+  vp8r::FrameParser parser;
+  vp8r_frame *own_frame = nullptr;  // scratch for vp8r_stream_decode
+  int mb_cols = 0, mb_rows = 0, width = 0, height = 0;
+  int pitch_y = 0, pitch_c = 0;
+  vp8r::Surface surf[5];
+  int ref[4] = {-1, -1, -1, -1};  // surface index of CURRENT(latest), LAST, GOLDEN, ALTREF
+  bool have_frame = false;
+};
+
+namespace {
+struct EventPair {
+  cudaEvent_t a, b;
+  int cls;
+};
+struct Slot {
+  DevFrameJob *h_jobs = nullptr, *d_jobs = nullptr;
+  int cap_jobs = 0;
+  uint8_t *d_arena = nullptr;
+  size_t arena_cap = 0;
+  cudaEvent_t done = nullptr;
+  bool pending = false;
+};
+}  // namespace
+
+struct vp8r_engine {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  bool own_stream = false;
+  Slot slots[2];
+  int cur_slot = 0;
+  // checksum scratch
+  DevFrameJob *h_cjobs = nullptr, *d_cjobs = nullptr;
+  unsigned long long *d_sums = nullptr, *h_sums = nullptr;
+  int cap_cjobs = 0;
+  // timing
+  bool timing = false;
+  std::vector<EventPair> live;
+  std::vector<EventPair> pool;
+  vp8r_timers acc{};
+};
+
+namespace {
+
+int EnsureDevice(vp8r_engine *e) {
+  CU_TRY(cudaSetDevice(e->device));
+  return VP8R_OK;
+}
+
+void FreeSurfaces(vp8r_stream *s) {
+  for (auto &sf : s->surf) {
+    if (sf.base) cudaFree(sf.base);
+    sf = vp8r::Surface{};
+  }
+}
+
+// (Re)allocates the stream's surface pool for a new frame size (key frames only; the reference
+// allocates a fresh Frame per frame, src/decode.cc:65-71).
+int ConfigureStream(vp8r_stream *s, const vp8r_frame_hdr &h) {
+  if (s->mb_cols == h.mb_cols && s->mb_rows == h.mb_rows && s->surf[0].base) {
+    s->width = h.width;
+    s->height = h.height;
+    return VP8R_OK;
+  }
+  CU_TRY(cudaStreamSynchronize(s->eng->st));
+  FreeSurfaces(s);
+  const int B = vp8r::kBorder;
+  const int wa = h.mb_cols * 16, ha = h.mb_rows * 16;
+  s->pitch_y = wa + 2 * B;
+  s->pitch_c = (wa / 2 + 2 * B + 15) & ~15;
+  const size_t ysz = (size_t(s->pitch_y) * (ha + 2 * B) + 255) & ~size_t(255);
+  const size_t csz = (size_t(s->pitch_c) * (ha / 2 + 2 * B) + 255) & ~size_t(255);
+  for (auto &sf : s->surf) {
+    void *p = nullptr;
+    cudaError_t err = cudaMalloc(&p, ysz + 2 * csz + 256);
+    if (err != cudaSuccess) {
+      SetError(std::string("cudaMalloc(surface): ") + cudaGetErrorString(err));
+      return VP8R_ERR_NOMEM;
+    }
+    sf.base = static_cast<uint8_t *>(p);
+    CU_TRY(cudaMemsetAsync(p, 0, ysz + 2 * csz + 256, s->eng->st));
+    sf.planes.y = sf.base + size_t(B) * s->pitch_y + B;
+    sf.planes.u = sf.base + ysz + size_t(B) * s->pitch_c + B;
+    sf.planes.v = sf.base + ysz + csz + size_t(B) * s->pitch_c + B;
+  }
+  s->mb_cols = h.mb_cols;
+  s->mb_rows = h.mb_rows;
+  s->width = h.width;
+  s->height = h.height;
+  s->ref[0] = s->ref[1] = s->ref[2] = s->ref[3] = -1;
+  s->have_frame = false;
+  return VP8R_OK;
+}
+
+int GrowSlot(vp8r_engine *e, Slot &sl, int n_jobs, size_t arena_bytes) {
+  if (n_jobs > sl.cap_jobs) {
+    int cap = std::max(n_jobs, sl.cap_jobs * 2);
+    cap = std::max(cap, 16);
+    CU_TRY(cudaStreamSynchronize(e->st));
+    if (sl.h_jobs) cudaFreeHost(sl.h_jobs);
+    if (sl.d_jobs) cudaFree(sl.d_jobs);
+    sl.h_jobs = nullptr;
+    sl.d_jobs = nullptr;
+    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_jobs), sizeof(DevFrameJob) * cap, cudaHostAllocDefault));
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&sl.d_jobs), sizeof(DevFrameJob) * cap));
+    sl.cap_jobs = cap;
+  }
+  if (arena_bytes > sl.arena_cap) {
+    size_t cap = std::max(arena_bytes + arena_bytes / 4, size_t(1) << 20);
+    CU_TRY(cudaStreamSynchronize(e->st));
+    if (sl.d_arena) cudaFree(sl.d_arena);
+    sl.d_arena = nullptr;
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&sl.d_arena), cap));
+    sl.arena_cap = cap;
+  }
+  return VP8R_OK;
+}
+
+EventPair GetPair(vp8r_engine *e, int cls) {
+  EventPair p;
+  if (!e->pool.empty()) {
+    p = e->pool.back();
+    e->pool.pop_back();
+  } else {
+    cudaEventCreate(&p.a);
+    cudaEventCreate(&p.b);
+  }
+  p.cls = cls;
+  return p;
+}
+
+struct ScopedTimer {
+  vp8r_engine *e;
+  EventPair p;
+  bool on;
+  ScopedTimer(vp8r_engine *eng, int cls) : e(eng), on(eng->timing) {
+    if (on) {
+      p = GetPair(e, cls);
+      cudaEventRecord(p.a, e->st);
+    }
+  }
+  ~ScopedTimer() {
+    if (on) {
+      cudaEventRecord(p.b, e->st);
+      e->live.push_back(p);
+    }
+  }
+};
+
+void DrainTimers(vp8r_engine *e) {
+  for (auto &p : e->live) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      switch (p.cls) {
+        case 0: e->acc.ms_inter += ms; break;
+        case 1: e->acc.ms_intra += ms; break;
+        case 2: e->acc.ms_filter += ms; break;
+        case 3: e->acc.ms_h2d += ms; break;
+        default: e->acc.ms_d2h += ms; break;
+      }
+    } else {
+      cudaGetLastError();
+    }
+    e->pool.push_back(p);
+  }
+  e->live.clear();
+}
+
+void FillJobSurfaces(const vp8r_stream *s, int cur, DevFrameJob *j) {
+  j->cur = s->surf[cur].planes;
+  for (int k = 1; k < 4; ++k) j->ref[k] = s->ref[k] >= 0 ? s->surf[s->ref[k]].planes : vp8r::DevPlanes{};
+  j->ref[0] = vp8r::DevPlanes{};
+  j->pitch_y = s->pitch_y;
+  j->pitch_c = s->pitch_c;
+  j->mb_cols = s->mb_cols;
+  j->mb_rows = s->mb_rows;
+  j->width = s->width;
+  j->height = s->height;
+}
+
+}  // namespace
+
+// ================================================================== C ABI ===================
+extern "C" {
+
+VP8R_API int vp8r_has_cuda(void) { return 1; }
+
+VP8R_API int vp8r_engine_create(int device, void *cuda_stream, vp8r_engine **out) {
+  if (!out) return VP8R_ERR_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    SetError("no CUDA device available: the reconstruction path has no CPU fallback");
+    return VP8R_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    SetError("device index out of range");
+    return VP8R_ERR_INVALID_ARG;
+  }
+  CU_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    SetError("libvp8r kernels are built for sm_100a only");
+    return VP8R_ERR_CUDA;
+  }
+  vp8r_engine *e = new (std::nothrow) vp8r_engine();
+  if (!e) return VP8R_ERR_NOMEM;
+  e->device = device;
+  if (cuda_stream) {
+    e->st = static_cast<cudaStream_t>(cuda_stream);
+  } else {
+    if (cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess) {
+      delete e;
+      SetError("cudaStreamCreate failed");
+      return VP8R_ERR_CUDA;
+    }
+    e->own_stream = true;
+  }
+  for (auto &sl : e->slots) cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+  err = vp8r::InitKernelTables();
+  if (err != cudaSuccess) {
+    SetError(std::string("kernel table upload: ") + cudaGetErrorString(err));
+    vp8r_engine_destroy(e);
+    return VP8R_ERR_CUDA;
+  }
+  *out = e;
+  return VP8R_OK;
+}
+
+VP8R_API void vp8r_engine_destroy(vp8r_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->st);
+  for (auto &sl : e->slots) {
+    if (sl.h_jobs) cudaFreeHost(sl.h_jobs);
+    if (sl.d_jobs) cudaFree(sl.d_jobs);
+    if (sl.d_arena) cudaFree(sl.d_arena);
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
+  if (e->h_cjobs) cudaFreeHost(e->h_cjobs);
+  if (e->d_cjobs) cudaFree(e->d_cjobs);
+  if (e->h_sums) cudaFreeHost(e->h_sums);
+  if (e->d_sums) cudaFree(e->d_sums);
+  DrainTimers(e);
+  for (auto &p : e->pool) {
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
+  }
+  if (e->own_stream) cudaStreamDestroy(e->st);
+  delete e;
+}
+
+VP8R_API int vp8r_engine_sync(vp8r_engine *e) {
+  if (!e) return VP8R_ERR_INVALID_ARG;
+  CU_TRY(cudaStreamSynchronize(e->st));
+  for (auto &sl : e->slots) sl.pending = false;
+  return VP8R_OK;
+}
+
+VP8R_API int vp8r_stream_open(vp8r_engine *e, vp8r_stream **out) {
+  if (!e || !out) return VP8R_ERR_INVALID_ARG;
+  vp8r_stream *s = new (std::nothrow) vp8r_stream();
+  if (!s) return VP8R_ERR_NOMEM;
+  s->eng = e;
+  *out = s;
+  return VP8R_OK;
+}
+
+VP8R_API void vp8r_stream_close(vp8r_stream *s) {
+  if (!s) return;
+  cudaSetDevice(s->eng->device);
+  cudaStreamSynchronize(s->eng->st);
+  FreeSurfaces(s);
+  delete s->own_frame;
+  delete s;
+}
+
+VP8R_API int vp8r_frame_upload(vp8r_engine *e, vp8r_frame *f) {
+  if (!e || !f || !f->blob) return VP8R_ERR_INVALID_ARG;
+  int rc = EnsureDevice(e);
+  if (rc) return rc;
+  f->DropDeviceCopy();
+  size_t bytes = f->used_bytes();
+  void *p = nullptr;
+  cudaError_t err = cudaMalloc(&p, bytes + 64);
+  if (err != cudaSuccess) {
+    SetError(std::string("cudaMalloc(frame): ") + cudaGetErrorString(err));
+    return VP8R_ERR_NOMEM;
+  }
+  err = cudaMemcpy(p, f->blob, bytes, cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    cudaFree(p);
+    SetError(std::string("cudaMemcpy(frame): ") + cudaGetErrorString(err));
+    return VP8R_ERR_CUDA;
+  }
+  f->d_blob = p;
+  f->d_bytes = bytes;
+  f->d_device = e->device;
+  return VP8R_OK;
+}
+
+VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *streams, vp8r_frame *const *frames) {
+  if (!e || n < 0 || (n > 0 && (!streams || !frames))) return VP8R_ERR_INVALID_ARG;
+  if (n == 0) return VP8R_OK;
+  int rc = EnsureDevice(e);
+  if (rc) return rc;
+
+  // Pass 1: validate, configure surfaces, size the staging arena.
+  size_t arena = 0;
+  for (int i = 0; i < n; ++i) {
+    vp8r_stream *s = streams[i];
+    vp8r_frame *f = frames[i];
+    if (!s || !f || s->eng != e || !f->blob) {
+      SetError("null stream/frame or stream of another engine");
+      return VP8R_ERR_INVALID_ARG;
+    }
+    const vp8r_frame_hdr &h = f->hdr;
+    if (h.key_frame) {
+      rc = ConfigureStream(s, h);
+      if (rc) return rc;
+    } else if (!s->have_frame || h.mb_cols != s->mb_cols || h.mb_rows != s->mb_rows) {
+      SetError("inter frame without matching reference frames");
+      return VP8R_ERR_STATE;
+    }
+    if (!(f->d_blob && f->d_device == e->device)) arena += (f->used_bytes() + 255) & ~size_t(255);
+  }
+  Slot &sl = e->slots[e->cur_slot];
+  e->cur_slot ^= 1;
+  if (sl.pending) {
+    CU_TRY(cudaEventSynchronize(sl.done));
+    sl.pending = false;
+  }
+  rc = GrowSlot(e, sl, n, arena);
+  if (rc) return rc;
+
+  // Pass 2: jobs + host->device staging.
+  int max_mbs = 0, max_rows = 0;
+  bool any_inter = false, any_intra = false;
+  size_t at = 0;
+  std::vector<int> cur_idx(n);
+  {
+    ScopedTimer t(e, 3);
+    for (int i = 0; i < n; ++i) {
+      vp8r_stream *s = streams[i];
+      vp8r_frame *f = frames[i];
+      const vp8r_frame_hdr &h = f->hdr;
+      // CURRENT = a surface no reference points at, and not the previous output.
+      int cur = -1;
+      for (int k = 0; k < 5 && cur < 0; ++k)
+        if (k != s->ref[0] && k != s->ref[1] && k != s->ref[2] && k != s->ref[3]) cur = k;
+      cur_idx[i] = cur;
+      DevFrameJob &j = sl.h_jobs[i];
+      std::memset(&j, 0, sizeof(j));
+      FillJobSurfaces(s, cur, &j);
+      const uint8_t *dev_blob;
+      if (f->d_blob && f->d_device == e->device) {
+        dev_blob = static_cast<const uint8_t *>(f->d_blob);
+      } else {
+        uint8_t *dst = sl.d_arena + at;
+        CU_TRY(cudaMemcpyAsync(dst, f->blob, f->used_bytes(), cudaMemcpyHostToDevice, e->st));
+        dev_blob = dst;
+        at += (f->used_bytes() + 255) & ~size_t(255);
+      }
+      j.mbs = reinterpret_cast<const vp8r_mb_info *>(dev_blob);
+      j.payload = reinterpret_cast<const int16_t *>(dev_blob + f->mb_bytes());
+      const int n_mb = int(h.mb_cols) * h.mb_rows;
+      j.n_inter = int(h.n_inter_mbs);
+      j.n_intra = n_mb - j.n_inter;
+      std::memcpy(j.dq, h.dq, sizeof(j.dq));
+      j.key_frame = h.key_frame;
+      j.version = h.version;
+      j.filter_type = h.filter_type;
+      j.lf_level = h.loop_filter_level;
+      j.sharpness = h.sharpness_level;
+      max_mbs = std::max(max_mbs, n_mb);
+      max_rows = std::max(max_rows, int(h.mb_rows));
+      any_inter |= j.n_inter > 0;
+      any_intra |= j.n_intra > 0;
+      e->acc.frames++;
+      e->acc.coef_blocks += h.n_coef_blocks;
+      e->acc.alg_bytes += uint64_t(n_mb) * 384 * (h.key_frame ? 1 : 2) + uint64_t(h.n_coef_blocks) * 32;
+    }
+    CU_TRY(cudaMemcpyAsync(sl.d_jobs, sl.h_jobs, sizeof(DevFrameJob) * n, cudaMemcpyHostToDevice, e->st));
+  }
+
+  if (any_inter) {
+    ScopedTimer t(e, 0);
+    CU_TRY(vp8r::LaunchInter(sl.d_jobs, n, max_mbs, e->st));
+    e->acc.launches_inter++;
+  }
+  if (any_intra) {
+    ScopedTimer t(e, 1);
+    CU_TRY(vp8r::LaunchIntra(sl.d_jobs, n, max_rows, e->st));
+    e->acc.launches_intra++;
+  }
+  {
+    ScopedTimer t(e, 2);
+    CU_TRY(vp8r::LaunchFilter(sl.d_jobs, n, max_rows, e->st));
+    e->acc.launches_filter++;
+  }
+  CU_TRY(cudaEventRecord(sl.done, e->st));
+  sl.pending = true;
+
+  // RefreshRefFrames (src/loop.h:19-46) on surface indices.
+  for (int i = 0; i < n; ++i) {
+    vp8r_stream *s = streams[i];
+    const vp8r_frame_hdr &h = frames[i]->hdr;
+    const int cur = cur_idx[i];
+    const bool g2a = !h.refresh_altref && h.copy_to_altref == 2;
+    const bool a2g = !h.refresh_golden && h.copy_to_golden == 2;
+    if (g2a && a2g) std::swap(s->ref[2], s->ref[3]);
+    else if (g2a) s->ref[3] = s->ref[2];
+    else if (a2g) s->ref[2] = s->ref[3];
+    if (h.refresh_golden) s->ref[2] = cur;
+    else if (h.copy_to_golden == 1) s->ref[2] = s->ref[1];
+    if (h.refresh_altref) s->ref[3] = cur;
+    else if (h.copy_to_altref == 1) s->ref[3] = s->ref[1];
+    if (h.refresh_last) s->ref[1] = cur;
+    s->ref[0] = cur;
+    s->have_frame = true;
+  }
+  return VP8R_OK;
+}
+
+VP8R_API size_t vp8r_stream_frame_bytes(const vp8r_stream *s) {
+  if (!s || !s->have_frame) return 0;
+  size_t cw = size_t(s->width + 1) / 2, ch = size_t(s->height + 1) / 2;
+  return size_t(s->width) * s->height + 2 * cw * ch;
+}
+
+VP8R_API int vp8r_stream_dims(const vp8r_stream *s, int *width, int *height) {
+  if (!s || !s->have_frame) return VP8R_ERR_STATE;
+  if (width) *width = s->width;
+  if (height) *height = s->height;
+  return VP8R_OK;
+}
+
+VP8R_API int vp8r_read_batch(vp8r_engine *e, int n, vp8r_stream *const *streams, uint8_t *const *dst,
+                             const size_t *cap, int async) {
+  if (!e || n < 0 || (n > 0 && (!streams || !dst))) return VP8R_ERR_INVALID_ARG;
+  int rc = EnsureDevice(e);
+  if (rc) return rc;
+  {
+    ScopedTimer t(e, 4);
+    for (int i = 0; i < n; ++i) {
+      const vp8r_stream *s = streams[i];
+      if (!s || s->eng != e || !s->have_frame || !dst[i]) {
+        SetError("stream has no reconstructed frame");
+        return VP8R_ERR_STATE;
+      }
+      const size_t need = vp8r_stream_frame_bytes(s);
+      if (cap && cap[i] < need) {
+        SetError("destination buffer too small");
+        return VP8R_ERR_INVALID_ARG;
+      }
+      // src/yuv.cc:6-28: crop to width x height, chroma ceil(w/2) x ceil(h/2), planes Y,U,V.
+      const vp8r::DevPlanes &p = s->surf[s->ref[0]].planes;
+      const size_t w = s->width, h = s->height, cw = (w + 1) / 2, ch = (h + 1) / 2;
+      uint8_t *o = dst[i];
+      CU_TRY(cudaMemcpy2DAsync(o, w, p.y, s->pitch_y, w, h, cudaMemcpyDeviceToHost, e->st));
+      CU_TRY(cudaMemcpy2DAsync(o + w * h, cw, p.u, s->pitch_c, cw, ch, cudaMemcpyDeviceToHost, e->st));
+      CU_TRY(cudaMemcpy2DAsync(o + w * h + cw * ch, cw, p.v, s->pitch_c, cw, ch, cudaMemcpyDeviceToHost, e->st));
+    }
+  }
+  if (!async) CU_TRY(cudaStreamSynchronize(e->st));
+  return VP8R_OK;
+}
+
+VP8R_API int vp8r_stream_read_frame(vp8r_stream *s, uint8_t *dst, size_t cap) {
+  if (!s) return VP8R_ERR_INVALID_ARG;
+  vp8r_stream *ss[1] = {s};
+  uint8_t *dd[1] = {dst};
+  size_t cc[1] = {cap};
+  return vp8r_read_batch(s->eng, 1, ss, dd, cc, 0);
+}
+
+VP8R_API int vp8r_checksum_batch(vp8r_engine *e, int n, vp8r_stream *const *streams, uint64_t *out) {
+  if (!e || n <= 0 || !streams || !out) return VP8R_ERR_INVALID_ARG;
+  int rc = EnsureDevice(e);
+  if (rc) return rc;
+  if (n > e->cap_cjobs) {
+    CU_TRY(cudaStreamSynchronize(e->st));
+    if (e->h_cjobs) cudaFreeHost(e->h_cjobs);
+    if (e->d_cjobs) cudaFree(e->d_cjobs);
+    if (e->h_sums) cudaFreeHost(e->h_sums);
+    if (e->d_sums) cudaFree(e->d_sums);
+    e->h_cjobs = e->d_cjobs = nullptr;
+    e->h_sums = e->d_sums = nullptr;
+    int cap = std::max(n, 64);
+    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_cjobs), sizeof(DevFrameJob) * cap, cudaHostAllocDefault));
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_cjobs), sizeof(DevFrameJob) * cap));
+    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_sums), sizeof(uint64_t) * cap, cudaHostAllocDefault));
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_sums), sizeof(uint64_t) * cap));
+    e->cap_cjobs = cap;
+  }
+  for (int i = 0; i < n; ++i) {
+    const vp8r_stream *s = streams[i];
+    if (!s || s->eng != e || !s->have_frame) {
+      SetError("stream has no reconstructed frame");
+      return VP8R_ERR_STATE;
+    }
+    DevFrameJob &j = e->h_cjobs[i];
+    std::memset(&j, 0, sizeof(j));
+    FillJobSurfaces(s, s->ref[0], &j);
+    j.checksum = e->d_sums + i;
+  }
+  CU_TRY(cudaMemsetAsync(e->d_sums, 0, sizeof(uint64_t) * n, e->st));
+  CU_TRY(cudaMemcpyAsync(e->d_cjobs, e->h_cjobs, sizeof(DevFrameJob) * n, cudaMemcpyHostToDevice, e->st));
+  CU_TRY(vp8r::LaunchChecksum(e->d_cjobs, n, e->st));
+  e->acc.launches_other++;
+  CU_TRY(cudaMemcpyAsync(e->h_sums, e->d_sums, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, e->st));
+  CU_TRY(cudaStreamSynchronize(e->st));
+  for (int i = 0; i < n; ++i) out[i] = e->h_sums[i];
+  return VP8R_OK;
+}
+
+VP8R_API int vp8r_stream_checksum(vp8r_stream *s, uint64_t *out) {
+  if (!s) return VP8R_ERR_INVALID_ARG;
+  vp8r_stream *ss[1] = {s};
+  return vp8r_checksum_batch(s->eng, 1, ss, out);
+}
+
+VP8R_API int vp8r_stream_decode(vp8r_stream *s, const uint8_t *data, size_t size, int *shown) {
+  if (!s || !data) return VP8R_ERR_INVALID_ARG;
+  if (!s->own_frame) {
+    s->own_frame = new (std::nothrow) vp8r_frame();
+    if (!s->own_frame) return VP8R_ERR_NOMEM;
+    s->own_frame->pinned = true;
+  }
+  // The staging copy of the previous call must have left the pinned blob before it is rewritten.
+  int rc = vp8r_engine_sync(s->eng);
+  if (rc) return rc;
+  rc = s->parser.Parse(data, size, s->own_frame);
+  if (rc) {
+    SetError(s->parser.error());
+    return rc;
+  }
+  if (shown) *shown = s->own_frame->hdr.show_frame;
+  vp8r_stream *ss[1] = {s};
+  vp8r_frame *ff[1] = {s->own_frame};
+  return vp8r_reconstruct_batch(s->eng, 1, ss, ff);
+}
+
+VP8R_API int vp8r_engine_set_timing(vp8r_engine *e, int enabled) {
+  if (!e) return VP8R_ERR_INVALID_ARG;
+  e->timing = enabled != 0;
+  return VP8R_OK;
+}
+
+VP8R_API int vp8r_engine_get_timers(vp8r_engine *e, vp8r_timers *out, int reset) {
+  if (!e || !out) return VP8R_ERR_INVALID_ARG;
+  int rc = vp8r_engine_sync(e);
+  if (rc) return rc;
+  DrainTimers(e);
+  *out = e->acc;
+  if (reset) e->acc = vp8r_timers{};
+  return VP8R_OK;
+}
+
+}  // extern "C"
