@@ -1,0 +1,317 @@
+#!/usr/bin/env python3
+"""bench.py -- decoded 1080p frames/s of the VP8 reconstruction path on N B200s.
+
+Workload (config.workload): S independent synthetic 1920x1080 streams per GPU, 30 frames each
+(1 key + 29 inter, six-tap MC, normal loop filter on, segmentation, golden/altref updates, one
+hidden alt-ref), written by tools/vp8synth.cc with seeds 7122+k.  A "step" decodes all S*30 frames
+of a GPU once.  Streams are independent, so N GPUs = N*S streams, no collective (scaling: weak).
+
+  value : frames/s with the parsed frames already resident in HBM (kernels only, CUDA events on
+          the launch stream, max over ranks)
+  e2e   : frames/s through the public API from compressed frames in host memory to cropped I420
+          in pinned host memory: host parse + H2D + kernels + D2H inside the timed region
+  roofline : algorithmic bytes (1.5*Wa*Ha*(1+is_inter) + 32*coded blocks per frame)
+          over the device time of the reconstruction kernels, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline : the reference decoder (oracle/_ref/decode, compiled unmodified from the
+          reference sources) on the host cores, one process per stream, on a bounded sample
+
+--impl reference times that CPU decoder alone (the reference has no GPU path).
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, FRAMES = 1920, 1080, 30
+FRAME_BYTES = W * H * 3 // 2
+SYNTH = os.path.join(ROOT, "vp8_b200", "_lib", "vp8synth")
+REF_DECODE = os.path.join(ROOT, "oracle", "_ref", "decode")
+SYNTH_ARGS = "--width 1920 --height 1080 --frames 30 --log2-parts 2 --q 40 --lf 24 --pct-skip 45 --coef-density 4"
+
+
+def synth_stream(seed, path, frames=FRAMES):
+    args = SYNTH_ARGS.replace("--frames 30", f"--frames {frames}").split()
+    subprocess.check_call([SYNTH] + args + ["--seed", str(seed), "--out", path])
+
+
+def peak_hbm():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].startswith("Active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
+
+
+def run_reference_cpu(paths, procs):
+    """Decodes `paths` with oracle/_ref/decode, `procs` processes at a time. Returns seconds."""
+    out_dir = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    t0 = time.perf_counter()
+    running, todo = [], list(enumerate(paths))
+    try:
+        while todo or running:
+            while todo and len(running) < procs:
+                k, p = todo.pop(0)
+                running.append(subprocess.Popen([REF_DECODE, p, os.path.join(out_dir, f"o{k % procs}.yuv")]))
+            running[0].wait()
+            if running[0].returncode != 0:
+                raise RuntimeError("reference decoder failed")
+            running.pop(0)
+    finally:
+        for r in running:
+            r.kill()
+        dt = time.perf_counter() - t0
+        shutil.rmtree(out_dir, ignore_errors=True)
+    return dt
+
+
+def cpu_sample(cores, frames_per_stream, tmp):
+    paths = []
+    for k in range(cores):
+        p = os.path.join(tmp, f"cpu{k}.ivf")
+        synth_stream(7122 + k, p, frames_per_stream)
+        paths.append(p)
+    return paths
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    if not os.path.exists(REF_DECODE):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/decode was not built"}))
+        return
+    cores = os.cpu_count() or 1
+    procs = min(cores, 64)
+    fps_list = []
+    with tempfile.TemporaryDirectory() as tmp:
+        n_frames = 6  # per stream and step: ~1 s of CPU per process
+        paths = cpu_sample(procs, n_frames, tmp)
+        times = []
+        for it in range(args.warmup + args.steps):
+            dt = run_reference_cpu(paths, procs)
+            if it >= args.warmup:
+                times.append(dt)
+        total = sum(times)
+        value = args.steps * procs * n_frames / total
+    line = {
+        "impl": "reference", "metric": "decoded 1080p frames/s", "value": value, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"reference CPU decoder, {procs} processes x one {n_frames}-frame 1080p synthetic stream per step",
+                   "mp_per_s": value * W * H / 1e6},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": procs, "kind": "reference",
+                         "sample": f"{procs} streams x {n_frames} frames per step, one process per stream"},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=64, help="independent 1080p streams per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import vp8_b200  # raises when libvp8r.so is missing: there is no fallback
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the reconstruction path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    S = args.streams
+    stream = torch.cuda.Stream()
+    eng = vp8_b200.Engine(local_rank, cuda_stream=stream.cuda_stream)
+    eng.set_timing(True)
+
+    # ---- inputs: S synthetic streams for this rank (untimed) ----
+    tmp = tempfile.mkdtemp()
+    payloads = []
+    for k in range(S):
+        p = os.path.join(tmp, f"s{k}.ivf")
+        synth_stream(7122 + rank * S + k, p)
+        payloads.append(vp8_b200.read_ivf(p)[1])
+    shutil.rmtree(tmp, ignore_errors=True)
+    ivf_bytes = sum(len(f) for p in payloads for f in p)
+
+    # ---- kernel-only: parse + upload every frame once, then replay ----
+    dec = vp8_b200.BatchDecoder(eng, S, pinned=False)
+    resident = []  # resident[t] = frames of time step t
+    shown_per_pass = 0
+    for t in range(FRAMES):
+        frames = []
+        for i in range(S):
+            f = dec.parsers[i].parse(payloads[i][t])
+            eng.upload(f)
+            shown_per_pass += f.desc().hdr.show_frame
+            frames.append(f)
+        resident.append(frames)
+
+    def device_pass():
+        for t in range(FRAMES):
+            eng.reconstruct_batch(dec.streams, resident[t])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        device_pass()
+    barrier()
+    eng.timers(reset=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            device_pass()
+        ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    tm = eng.timers(reset=True)
+    sums = eng.checksum_batch(dec.streams)  # last frame of every stream, compared below with the e2e pass
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    frames_per_step = S * FRAMES
+    value = world * frames_per_step * args.steps / (ms / 1e3)
+
+    kern_ms = tm.ms_inter + tm.ms_intra + tm.ms_filter
+    peak, peak_kind = peak_hbm()
+    achieved = tm.alg_bytes / (kern_ms / 1e3) / 1e9 if kern_ms > 0 else 0.0
+    shares = {"inter": tm.ms_inter, "intra": tm.ms_intra, "filter": tm.ms_filter}
+    dominant = max(shares, key=shares.get)
+    n_launch = {"inter": tm.launches_inter, "intra": tm.launches_intra, "filter": tm.launches_filter}
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_kind": peak_kind, "dominant_kernel": dominant,
+                "kernel_ms": {k: round(v, 3) for k, v in shares.items()},
+                "dominant_avg_launch_ms": shares[dominant] / max(1, n_launch[dominant]),
+                "alg_bytes_per_frame": tm.alg_bytes / max(1, tm.frames)}
+    launches = tm.launches_inter + tm.launches_intra + tm.launches_filter
+
+    # ---- end to end: compressed frames in host memory -> cropped I420 in pinned host memory ----
+    for f in (f for fr in resident for f in fr):
+        f.close()
+    dec.close()
+    e2e_dec = vp8_b200.BatchDecoder(eng, S, pinned=True)
+    ring_t = [torch.empty((S, FRAME_BYTES), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    ring = [[(ring_t[k][i].data_ptr(), FRAME_BYTES) for i in range(S)] for k in range(2)]
+    e2e_dec.decode(payloads, out_ring=ring)  # warm-up (allocations, pinned buffers growth)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_dec.reset()
+        decoded, shown, h2d, d2h = e2e_dec.decode(payloads, out_ring=ring)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_sums = eng.checksum_batch(e2e_dec.streams)
+    if e2e_sums != sums:
+        raise SystemExit("bench: device-resident replay and end-to-end pass disagree on the final frames")
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * frames_per_step * args.e2e_steps / e2e_s
+    tm2 = eng.timers(reset=True)
+    e2e_dec.close()
+    eng.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_DECODE):
+        cores = min(os.cpu_count() or 1, 64)
+        with tempfile.TemporaryDirectory() as td:
+            n_fr = 10
+            paths = cpu_sample(cores, n_fr, td)
+            dt = run_reference_cpu(paths, cores)
+        cpu = {"value": cores * n_fr / dt, "unit": "frames/s", "cores": cores, "kind": "reference",
+               "sample": f"{cores} synthetic 1080p streams x {n_fr} frames, one oracle/_ref/decode process per core, {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "decoded 1080p frames/s", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"{S} independent synthetic 1920x1080 30-frame VP8 streams per GPU (vp8synth seeds 7122+k: "
+                                   "1 key + 29 inter frames, six-tap MC, normal loop filter level 24, segmentation, "
+                                   "golden/altref updates, 4 DCT partitions), decoded in lock-step batches of one frame per stream",
+                       "streams_per_gpu": S, "frames_per_stream": FRAMES, "mp_per_s": value * W * H / 1e6,
+                       "compressed_bytes_per_step": ivf_bytes, "shown_frames_per_step": shown_per_pass,
+                       "l2_policy": "inputs larger than L2 (one batch touches ~%d MB of surfaces and side data)" % (S * 8),
+                       "parse_threads": e2e_dec.parse_threads},
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "mp_per_s": e2e_value * W * H / 1e6, "steps": args.e2e_steps,
+                    "kernel_ms_per_step": (tm2.ms_inter + tm2.ms_intra + tm2.ms_filter) / max(1, args.e2e_steps + 1)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -13,7 +13,7 @@ $NVCC $ARCH -lineinfo $CXXFLAGS -Xcompiler -fPIC,-fvisibility=hidden -c vp8_b200
 g++ $CXXFLAGS -fPIC -fvisibility=hidden -Wall -Wextra -c vp8_b200/csrc/host/frame_parser.cc -o vp8_b200/_build/frame_parser.o
 g++ $CXXFLAGS -fPIC -fvisibility=hidden -Wall -Wextra -c vp8_b200/csrc/capi.cc -o vp8_b200/_build/capi.o
 $NVCC $ARCH -shared -o "$OUT/libvp8r.so" vp8_b200/_build/recon_kernels.o vp8_b200/_build/engine.o \
-    vp8_b200/_build/frame_parser.o vp8_b200/_build/capi.o
+    vp8_b200/_build/frame_parser.o vp8_b200/_build/capi.o -lpthread
 if [ -f tools/vp8synth.cc ]; then
   g++ -O2 -std=c++17 -Wall -Wextra tools/vp8synth.cc -o "$OUT/vp8synth"
 fi

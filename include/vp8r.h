@@ -134,6 +134,12 @@ VP8R_API int vp8r_frame_get_desc(const vp8r_frame *f, vp8r_frame_desc *out);
 /* Parses one compressed frame (the payload of one IVF frame record) into `out`. */
 VP8R_API int vp8r_parser_parse(vp8r_parser *p, const uint8_t *data, size_t size, vp8r_frame *out);
 
+/* Parses frame i with parsers[i] into out[i] for i < n, using up to n_threads host threads
+ * (parsers must be distinct).  status (nullable) receives the per-frame result; the return value
+ * is the first failure. */
+VP8R_API int vp8r_parse_batch(int n, vp8r_parser *const *parsers, const uint8_t *const *data,
+                              const size_t *sizes, vp8r_frame *const *out, int n_threads, int *status);
+
 /* Peeks at the 3-byte frame tag: key-frame flag (bit 0 of byte 0 clear, bitstream_parser.cc:19-20).
  * Used to cut a stream at key frames (src/display.cc:64-67 does the same to seek). */
 VP8R_API int vp8r_is_key_frame(const uint8_t *data, size_t size);
@@ -150,6 +156,13 @@ typedef struct vp8r_stream vp8r_stream;
 VP8R_API int vp8r_engine_create(int device, void *cuda_stream, vp8r_engine **out);
 VP8R_API void vp8r_engine_destroy(vp8r_engine *e);
 VP8R_API int vp8r_engine_sync(vp8r_engine *e);
+
+/* Fences for pipelining host work against the asynchronous device work: a ticket marks everything
+ * submitted to the engine so far; vp8r_engine_wait blocks the host until that work is done (so a
+ * pinned vp8r_frame or output buffer can be reused).  At most 16 tickets are outstanding; waiting
+ * on an older one waits for nothing (a later fence was recorded over it - callers keep <= 16). */
+VP8R_API int vp8r_engine_fence(vp8r_engine *e, uint64_t *ticket);
+VP8R_API int vp8r_engine_wait(vp8r_engine *e, uint64_t ticket);
 
 VP8R_API int vp8r_stream_open(vp8r_engine *e, vp8r_stream **out);
 VP8R_API void vp8r_stream_close(vp8r_stream *s);

@@ -103,3 +103,25 @@ def ref_decode_ivf(path):
     with tempfile.NamedTemporaryFile(suffix=".yuv") as t:
         subprocess.check_call([REF_DECODE, path, t.name])
         return open(t.name, "rb").read()
+
+
+SYNTH_BIN = os.path.join(ROOT, "vp8_b200", "_lib", "vp8synth")
+
+
+def synth_manifest():
+    import json
+    return json.load(open(os.path.join(SYN_DIR, "manifest.json")))
+
+
+def synth_stream(args):
+    """Runs vp8synth with `args` (str) and returns the IVF bytes."""
+    import tempfile
+    ensure_built()
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "s.ivf")
+        subprocess.check_call([SYNTH_BIN] + args.split() + ["--out", p])
+        return open(p, "rb").read()
+
+
+def synth_golden(name):
+    return [l.split()[0] for l in open(os.path.join(SYN_DIR, name + ".md5"))]

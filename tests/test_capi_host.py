@@ -1,0 +1,134 @@
+"""CPU tier: the C-ABI library loads, exports every symbol include/vp8r.h declares, and the host
+logic (parser errors, key-frame scan, checksum, transforms KATs) behaves.  No compute calls."""
+import ctypes as C
+import os
+import re
+import random
+
+import pytest
+
+import helpers
+
+
+def test_header_and_library_agree(built):
+    from vp8_b200 import _capi
+    hdr = open(os.path.join(helpers.ROOT, "include", "vp8r.h")).read()
+    declared = set(re.findall(r"VP8R_API\s+[\w \*]+?\b(vp8r_\w+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = C.CDLL(helpers.LIB_SO)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in vp8r.h but not exported"
+    assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
+
+
+def test_struct_layout(built):
+    from vp8_b200 import _capi
+    assert C.sizeof(_capi.MbInfo) == 32
+    assert C.sizeof(_capi.FrameHdr) == 8 + 16 + 48 + 16
+
+
+def test_engine_fails_loudly_without_gpu(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import vp8_b200
+    with pytest.raises(vp8_b200._capi.Vp8rError) as e:
+        vp8_b200.Engine(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_parser_errors(built):
+    import vp8_b200
+    from vp8_b200._capi import Vp8rError
+    _, payloads = vp8_b200.read_ivf(helpers.vectors()[0])
+    key = payloads[0]
+    p = vp8_b200.Parser()
+    with pytest.raises(Vp8rError) as e:  # inter frame before any key frame (VP8R_ERR_STATE)
+        p.parse(bytes([key[0] | 1]) + key[1:])
+    assert e.value.code == 5
+    with pytest.raises(Vp8rError) as e:  # bad start code: ensure() in bitstream_parser.cc:28-29
+        p.parse(key[:3] + b"\x00\x00\x00" + key[6:])
+    assert e.value.code == 2
+    with pytest.raises(Vp8rError) as e:  # experimental version: bitstream_parser.cc:24-25
+        p.parse(bytes([key[0] | (4 << 1)]) + key[1:])
+    assert e.value.code == 3
+    with pytest.raises(Vp8rError) as e:  # truncated: the reference throws std::out_of_range
+        p.parse(key[:len(key) // 3])
+    assert e.value.code == 4
+    with pytest.raises(Vp8rError):
+        p.parse(b"")
+    # and the parser still works afterwards
+    d = p.parse(key).desc()
+    assert d.hdr.key_frame == 1 and d.hdr.mb_cols == 11 and d.hdr.mb_rows == 9
+
+
+def test_key_frame_scan(built):
+    import vp8_b200
+    lib = vp8_b200._capi.load()
+    _, payloads = vp8_b200.read_ivf(os.path.join(helpers.VEC_DIR, "vp80-02-inter-1402.ivf"))
+    flags = [lib.vp8r_is_key_frame(p, len(p)) for p in payloads]
+    assert flags[0] == 1 and sum(flags) >= 1 and 0 in flags
+
+
+def test_checksum_host(built):
+    import vp8_b200
+    lib = vp8_b200._capi.load()
+    w, h = 7, 5
+    n = helpers.i420_bytes(w, h)
+    data = bytes((i * 37 + 11) & 255 for i in range(n))
+    s1 = sum(data) & 0xFFFFFFFF
+    s2 = sum((i + 1) * b for i, b in enumerate(data)) & 0xFFFFFFFF
+    assert lib.vp8r_checksum_i420(data, w, h) == (s2 << 32) | s1
+
+
+def test_transform_kats(built):
+    """The reference's own unit tests (test/dct_test.h:16-71): a DC-only block inverse-transforms
+    to (dc+4)>>3 everywhere; here checked on the oracle's IDCT (the CUDA IDCT is checked against
+    the oracle on the GPU)."""
+    orc = helpers.Oracle()
+    rng = random.Random(7122)
+    for _ in range(100):
+        dc = rng.randrange(-2048, 2048)
+        blk = (C.c_int16 * 16)(dc, *([0] * 15))
+        orc.lib.oracle_idct4x4(blk)
+        assert list(blk) == [(dc + 4) >> 3] * 16
+    # IWHT of a DC-only block: every output (dc+3)>>3
+    for _ in range(100):
+        dc = rng.randrange(-2048, 2048)
+        blk = (C.c_int16 * 16)(dc, *([0] * 15))
+        orc.lib.oracle_iwht4x4(blk)
+        assert list(blk) == [(dc + 3) >> 3] * 16
+    orc.close()
+
+
+def test_parsed_frame_accounting(built):
+    """coef_mask / coef_offset / n_payload_blocks are mutually consistent for every frame of a
+    stream that uses SPLIT motion vectors."""
+    import vp8_b200
+    ivf = helpers.synth_stream("--width 176 --height 144 --frames 6 --seed 11 --pct-split 40")
+    _, payloads = vp8_b200.read_ivf(ivf)
+    p = vp8_b200.Parser()
+    for pl in payloads:
+        fr = p.parse(pl)
+        d = fr.desc()
+        n_mb = d.hdr.mb_cols * d.hdr.mb_rows
+        at = 0
+        coef = split = inter = 0
+        for i in range(n_mb):
+            mb = d.mbs[i]
+            is_split = (mb.flags & 1) and ((mb.flags >> 3) & 7) == 4
+            if is_split:
+                assert mb.aux[0] == at
+                at += 2
+                split += 1
+            inter += mb.flags & 1
+            assert mb.coef_offset == at
+            k = bin(mb.coef_mask).count("1")
+            at += k
+            coef += k
+            assert mb.coef_mask < (1 << 25)
+            if not (mb.flags & 0x100):
+                assert not (mb.coef_mask & 1)  # no Y2 block without has_y2
+        assert at == d.hdr.n_payload_blocks and coef == d.hdr.n_coef_blocks
+        assert split == d.hdr.n_split_mbs and inter == d.hdr.n_inter_mbs
+        fr.close()

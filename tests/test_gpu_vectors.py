@@ -81,3 +81,16 @@ def test_all_vectors_batched(engine):
     finally:
         for s in streams:
             s.close()
+
+
+@pytest.mark.parametrize("name", sorted(helpers.synth_manifest().keys()))
+def test_synthetic_streams_match_reference_md5(engine, name):
+    """Synthetic streams (bilinear, full-pixel, simple filter, hidden alt-ref, multi-partition,
+    1080p) against MD5s produced by the unmodified reference decoder."""
+    import vp8_b200
+    m = helpers.synth_manifest()[name]
+    frames = vp8_b200.decode_ivf(helpers.synth_stream(m["args"]), engine=engine)
+    gold = helpers.synth_golden(name)
+    assert len(frames) == len(gold)
+    for k, (img, md5) in enumerate(zip(frames, gold)):
+        assert helpers.md5(img) == md5, f"{name} shown frame {k}"

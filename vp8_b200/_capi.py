@@ -44,10 +44,14 @@ SIGNATURES = {
     "vp8r_frame_destroy": (None, [C.c_void_p]),
     "vp8r_frame_get_desc": (C.c_int, [C.c_void_p, C.POINTER(FrameDesc)]),
     "vp8r_parser_parse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vp8r_parse_batch": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                   C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int)]),
     "vp8r_is_key_frame": (C.c_int, [C.c_void_p, C.c_size_t]),
     "vp8r_engine_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "vp8r_engine_destroy": (None, [C.c_void_p]),
     "vp8r_engine_sync": (C.c_int, [C.c_void_p]),
+    "vp8r_engine_fence": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "vp8r_engine_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
     "vp8r_stream_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "vp8r_stream_close": (None, [C.c_void_p]),
     "vp8r_frame_upload": (C.c_int, [C.c_void_p, C.c_void_p]),

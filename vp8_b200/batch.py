@@ -1,0 +1,90 @@
+"""Lock-step decoding of many independent streams: the throughput-oriented public API.
+
+All streams advance one frame per time step; the frames of one time step are parsed on host
+threads (vp8r_parse_batch), reconstructed by one batched launch per kernel class
+(vp8r_reconstruct_batch) and, optionally, copied back as cropped I420 (vp8r_read_batch).  Host
+parsing of step t+1 overlaps the device work of step t; fences guard the reuse of pinned buffers.
+"""
+import ctypes as C
+import os
+
+from . import _capi
+from ._capi import check
+from .decoder import ParsedFrame, Parser
+
+
+class BatchDecoder:
+    def __init__(self, engine, n_streams, parse_threads=None, pinned=True):
+        self.engine = engine
+        self._lib = engine._lib
+        self.n = n_streams
+        self.parse_threads = parse_threads or min(n_streams, os.cpu_count() or 1)
+        self.parsers = [Parser() for _ in range(n_streams)]
+        self.streams = [engine.open_stream() for _ in range(n_streams)]
+        self.slots = [[ParsedFrame(pinned=pinned) for _ in range(n_streams)] for _ in range(2)]
+
+    def reset(self):
+        for p in self.parsers:
+            p.reset()
+
+    def parse_step(self, slot, payloads, live):
+        """Parses payloads[i] (bytes) of the live streams into slot `slot`.  Returns the frames."""
+        n = len(live)
+        bufs = [(C.c_uint8 * len(payloads[i])).from_buffer_copy(payloads[i]) for i in live]
+        pa = (C.c_void_p * n)(*[self.parsers[i].handle for i in live])
+        da = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
+        sa = (C.c_size_t * n)(*[len(payloads[i]) for i in live])
+        frames = [self.slots[slot][i] for i in live]
+        fa = (C.c_void_p * n)(*[f.handle for f in frames])
+        check(self._lib.vp8r_parse_batch(n, pa, da, sa, fa, self.parse_threads, None))
+        return frames
+
+    def fence(self):
+        t = C.c_uint64()
+        check(self._lib.vp8r_engine_fence(self.engine.handle, C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        check(self._lib.vp8r_engine_wait(self.engine.handle, ticket))
+
+    def decode(self, payloads, out_ring=None, on_step=None):
+        """payloads[s] = list of compressed frames of stream s.  out_ring: optional list of two lists
+        of (ptr, capacity) pinned host buffers, one per stream, that receive the frames of a time step
+        (ring of two steps).  on_step(t, live, frames) is called after step t has been submitted.
+        Returns (frames decoded, frames shown, h2d bytes, d2h bytes)."""
+        steps = max(len(p) for p in payloads)
+        decoded = shown = h2d = d2h = 0
+        tickets = {}
+        live = [i for i in range(self.n) if len(payloads[i]) > 0]
+        frames = self.parse_step(0, [p[0] if p else b"" for p in payloads], live)
+        for t in range(steps):
+            streams = [self.streams[i] for i in live]
+            self.engine.reconstruct_batch(streams, frames)
+            decoded += len(live)
+            for f in frames:
+                d = f.desc()
+                h2d += d.hdr.mb_cols * d.hdr.mb_rows * 32 + d.hdr.n_payload_blocks * 32
+                shown += d.hdr.show_frame
+            if out_ring is not None:
+                ring = out_ring[t & 1]
+                self.engine.read_batch(streams, [ring[i][0] for i in live], [ring[i][1] for i in live], async_=True)
+                d2h += sum(s.frame_bytes() for s in streams)
+            tickets[t] = self.fence()
+            if on_step:
+                on_step(t, live, frames)
+            if t + 1 < steps:
+                if t - 1 in tickets:
+                    self.wait(tickets.pop(t - 1))  # slot (t+1)&1 and ring (t+1)&1 are free again
+                live = [i for i in range(self.n) if len(payloads[i]) > t + 1]
+                frames = self.parse_step((t + 1) & 1, [p[t + 1] if len(p) > t + 1 else b"" for p in payloads], live)
+        self.engine.sync()
+        return decoded, shown, h2d, d2h
+
+    def close(self):
+        for s in self.streams:
+            s.close()
+        for p in self.parsers:
+            p.close()
+        for sl in self.slots:
+            for f in sl:
+                f.close()

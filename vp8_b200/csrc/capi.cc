@@ -1,8 +1,11 @@
 // Host-only part of the C ABI: parser, parsed-frame objects, checksums, error reporting.
 // (The engine half lives in rt/engine.cu.)
+#include <atomic>
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "host/frame_parser.h"
 #include "host/parsed_frame.h"
@@ -48,6 +51,41 @@ VP8R_API int vp8r_parser_parse(vp8r_parser *p, const uint8_t *data, size_t size,
   int rc = p->impl.Parse(data, size, out);
   if (rc != VP8R_OK) vp8r::SetError(p->impl.error());
   return rc;
+}
+
+// Parses n frames of n DIFFERENT streams concurrently (one parser per stream; the bool decoder is
+// serial within a stream, so stream-level parallelism is what the host has).
+VP8R_API int vp8r_parse_batch(int n, vp8r_parser *const *parsers, const uint8_t *const *data, const size_t *sizes,
+                              vp8r_frame *const *out, int n_threads, int *status) {
+  if (n < 0 || (n > 0 && (!parsers || !data || !sizes || !out))) return VP8R_ERR_INVALID_ARG;
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > n) n_threads = n;
+  std::atomic<int> next(0), first_err(VP8R_OK);
+  std::vector<std::string> errs(static_cast<size_t>(n_threads));
+  auto work = [&](int tid) {
+    for (;;) {
+      int i = next.fetch_add(1);
+      if (i >= n) break;
+      int rc = (parsers[i] && out[i]) ? parsers[i]->impl.Parse(data[i], sizes[i], out[i]) : VP8R_ERR_INVALID_ARG;
+      if (status) status[i] = rc;
+      if (rc != VP8R_OK) {
+        int expected = VP8R_OK;
+        if (first_err.compare_exchange_strong(expected, rc)) errs[size_t(tid)] = parsers[i] ? parsers[i]->impl.error() : "null";
+      }
+    }
+  };
+  if (n_threads <= 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto &t : pool) t.join();
+  }
+  if (first_err.load() != VP8R_OK)
+    for (auto &e : errs)
+      if (!e.empty()) vp8r::SetError(e);
+  return first_err.load();
 }
 
 VP8R_API int vp8r_is_key_frame(const uint8_t *data, size_t size) {

@@ -98,6 +98,9 @@ struct vp8r_engine {
   DevFrameJob *h_cjobs = nullptr, *d_cjobs = nullptr;
   unsigned long long *d_sums = nullptr, *h_sums = nullptr;
   int cap_cjobs = 0;
+  // host-visible fences (vp8r_engine_fence / vp8r_engine_wait)
+  cudaEvent_t fence_ev[16] = {};
+  uint64_t fence_head = 0;
   // timing
   bool timing = false;
   std::vector<EventPair> live;
@@ -309,6 +312,8 @@ VP8R_API void vp8r_engine_destroy(vp8r_engine *e) {
   if (e->d_cjobs) cudaFree(e->d_cjobs);
   if (e->h_sums) cudaFreeHost(e->h_sums);
   if (e->d_sums) cudaFree(e->d_sums);
+  for (auto &ev : e->fence_ev)
+    if (ev) cudaEventDestroy(ev);
   DrainTimers(e);
   for (auto &p : e->pool) {
     cudaEventDestroy(p.a);
@@ -607,6 +612,29 @@ VP8R_API int vp8r_stream_decode(vp8r_stream *s, const uint8_t *data, size_t size
   vp8r_stream *ss[1] = {s};
   vp8r_frame *ff[1] = {s->own_frame};
   return vp8r_reconstruct_batch(s->eng, 1, ss, ff);
+}
+
+VP8R_API int vp8r_engine_fence(vp8r_engine *e, uint64_t *ticket) {
+  if (!e || !ticket) return VP8R_ERR_INVALID_ARG;
+  int rc = EnsureDevice(e);
+  if (rc) return rc;
+  const uint64_t t = e->fence_head++;
+  cudaEvent_t &ev = e->fence_ev[t & 15];
+  if (!ev) CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CU_TRY(cudaEventRecord(ev, e->st));
+  *ticket = t;
+  return VP8R_OK;
+}
+
+VP8R_API int vp8r_engine_wait(vp8r_engine *e, uint64_t ticket) {
+  if (!e) return VP8R_ERR_INVALID_ARG;
+  if (ticket >= e->fence_head) {
+    SetError("unknown fence ticket");
+    return VP8R_ERR_INVALID_ARG;
+  }
+  if (e->fence_head - ticket > 16) return VP8R_OK;  // recycled: a later fence on the same stream was recorded over it
+  CU_TRY(cudaEventSynchronize(e->fence_ev[ticket & 15]));
+  return VP8R_OK;
 }
 
 VP8R_API int vp8r_engine_set_timing(vp8r_engine *e, int enabled) {
