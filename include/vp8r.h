@@ -101,6 +101,13 @@ typedef struct vp8r_frame_hdr {
   uint32_t n_payload_blocks;  /* all 32-byte payload blocks (coefficients + SPLIT motion vectors) */
   uint32_t n_inter_mbs;       /* informational */
   uint32_t n_split_mbs;       /* informational */
+  /* Dependency levels of the intra macroblocks of an inter frame (0 when the frame has none or too
+   * many levels, e.g. key frames, which are scheduled as a wavefront instead).  An intra MB of
+   * level L only neighbours (left, above-left, above, above-right) intra MBs of lower levels, so
+   * all MBs of one level can be predicted concurrently.  The table lives in the payload at block
+   * `intra_levels_at`: n_intra_levels+1 uint32 offsets, then the MB indices sorted by level. */
+  uint32_t n_intra_levels;
+  uint32_t intra_levels_at;
 } vp8r_frame_hdr;
 
 typedef struct vp8r_frame_desc {

@@ -24,7 +24,7 @@ def test_header_and_library_agree(built):
 def test_struct_layout(built):
     from vp8_b200 import _capi
     assert C.sizeof(_capi.MbInfo) == 32
-    assert C.sizeof(_capi.FrameHdr) == 8 + 16 + 48 + 16
+    assert C.sizeof(_capi.FrameHdr) == 8 + 16 + 48 + 24
 
 
 def test_engine_fails_loudly_without_gpu(built):
@@ -129,6 +129,6 @@ def test_parsed_frame_accounting(built):
             assert mb.coef_mask < (1 << 25)
             if not (mb.flags & 0x100):
                 assert not (mb.coef_mask & 1)  # no Y2 block without has_y2
-        assert at == d.hdr.n_payload_blocks and coef == d.hdr.n_coef_blocks
+        assert at == (d.hdr.intra_levels_at if d.hdr.n_intra_levels else d.hdr.n_payload_blocks) and coef == d.hdr.n_coef_blocks
         assert split == d.hdr.n_split_mbs and inter == d.hdr.n_inter_mbs
         fr.close()

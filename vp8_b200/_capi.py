@@ -20,7 +20,8 @@ class FrameHdr(C.Structure):
                 ("sign_bias_golden", C.c_uint8), ("sign_bias_altref", C.c_uint8), ("reserved0", C.c_uint8 * 3),
                 ("dq", (C.c_int16 * 6) * 4),
                 ("n_coef_blocks", C.c_uint32), ("n_payload_blocks", C.c_uint32),
-                ("n_inter_mbs", C.c_uint32), ("n_split_mbs", C.c_uint32)]
+                ("n_inter_mbs", C.c_uint32), ("n_split_mbs", C.c_uint32),
+                ("n_intra_levels", C.c_uint32), ("intra_levels_at", C.c_uint32)]
 
 
 class FrameDesc(C.Structure):

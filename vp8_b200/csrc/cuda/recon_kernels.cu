@@ -410,7 +410,7 @@ __device__ __forceinline__ void PublishRow(volatile int *progress, int row, int 
 // ------------------------------------------------------------------------------------------
 // K_intra
 // ------------------------------------------------------------------------------------------
-struct IntraScratch {
+struct __align__(16) IntraScratch {
   short y2[16];
   short res[24][16];
   unsigned char tile[17][24];  // B_PRED working tile: row 0 = row above, column 3 = column left,
@@ -559,10 +559,36 @@ __device__ __forceinline__ void PredictBpred(const DevFrameJob &job, int mb_r, i
   }
 }
 
+// One intra macroblock by one warp: residual, then chroma / 16x16 luma per 4x4 block, then B_PRED.
+__device__ __forceinline__ void IntraMacroblock(const DevFrameJob &job, int r, int c, int lane, IntraScratch &s,
+                                                const unsigned short *lut, volatile int *progress) {
+  vp8r_mb_info mb;
+  {
+    const int4 *p = reinterpret_cast<const int4 *>(job.mbs + r * job.mb_cols + c);
+    int4 a = __ldg(p), b = __ldg(p + 1);
+    mb.flags = a.x; mb.coef_mask = a.y; mb.coef_offset = a.z;
+    mb.aux[0] = b.x; mb.aux[1] = b.y;
+  }
+  int res[16];
+  const bool has_res = WarpResidual(job, mb, lane, s.y2, res);
+  const unsigned res_mask = __ballot_sync(0xffffffffu, has_res);
+  if (lane < 24) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s.res[lane][i] = (short)res[i];
+  }
+  // Everything above and to the left must be final (unfiltered) pixels of this frame.
+  if (progress) WaitRow(progress, r - 1, min(c + 2, job.mb_cols));
+  __syncwarp();
+  const int ymode = (mb.flags >> VP8R_MB_MODE_SHIFT) & 7, uvmode = (mb.flags >> VP8R_MB_UVMODE_SHIFT) & 3;
+  PredictMbBlock(job, r, c, lane, ymode, uvmode, ymode != 4, lane < 24 ? s.res[lane] : s.res[0], has_res);
+  if (ymode == 4) PredictBpred(job, r, c, lane, mb, s, res_mask, lut);
+}
+
+// Wavefront variant: frames whose intra macroblocks form long dependency chains (key frames).
 __global__ void __launch_bounds__(kWaveWarps * 32) IntraKernel(const DevFrameJob *__restrict__ jobs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const DevFrameJob &job = jobs[blockIdx.x];
-  if (job.n_intra == 0) return;
+  if (job.n_intra == 0 || job.n_intra_levels != 0) return;
   const int rows = job.mb_rows, cols = job.mb_cols;
   volatile int *progress = reinterpret_cast<volatile int *>(smem_raw);
   unsigned short *lut = reinterpret_cast<unsigned short *>(smem_raw + ((rows * 4 + 15) & ~15));
@@ -583,31 +609,38 @@ __global__ void __launch_bounds__(kWaveWarps * 32) IntraKernel(const DevFrameJob
         const int k = __ffs(intra_mask) - 1;
         intra_mask &= intra_mask - 1;
         const int c = c0 + k;
-        vp8r_mb_info mb;
-        {
-          const int4 *p = reinterpret_cast<const int4 *>(job.mbs + r * cols + c);
-          int4 a = __ldg(p), b = __ldg(p + 1);
-          mb.flags = a.x; mb.coef_mask = a.y; mb.coef_offset = a.z;
-          mb.aux[0] = b.x; mb.aux[1] = b.y;
-        }
-        int res[16];
-        const bool has_res = WarpResidual(job, mb, lane, s.y2, res);
-        const unsigned res_mask = __ballot_sync(0xffffffffu, has_res);
-        if (lane < 24) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) s.res[lane][i] = (short)res[i];
-        }
-        // Everything above and to the left must be final (unfiltered) pixels of this frame.
-        WaitRow(progress, r - 1, min(c + 2, cols));
-        __syncwarp();
-        const int ymode = (mb.flags >> VP8R_MB_MODE_SHIFT) & 7, uvmode = (mb.flags >> VP8R_MB_UVMODE_SHIFT) & 3;
-        PredictMbBlock(job, r, c, lane, ymode, uvmode, ymode != 4, lane < 24 ? s.res[lane] : s.res[0], has_res);
-        if (ymode == 4) PredictBpred(job, r, c, lane, mb, s, res_mask, lut);
+        IntraMacroblock(job, r, c, lane, s, lut, progress);
         PublishRow(progress, r, c + 1, lane);
       }
       PublishRow(progress, r, min(c0 + 32, cols), lane);
     }
   }
+}
+
+// Flat variant: all intra macroblocks of dependency level `level` of every frame, one warp each.
+// Levels are launched in increasing order; macroblocks of one level never neighbour each other.
+constexpr int kFlatWarps = 8;
+__global__ void __launch_bounds__(kFlatWarps * 32) IntraFlatKernel(const DevFrameJob *__restrict__ jobs, int level) {
+  __shared__ __align__(16) unsigned short lut[160];
+  __shared__ IntraScratch scratch[kFlatWarps];
+  const DevFrameJob &job = jobs[blockIdx.y];
+  if (level >= job.n_intra_levels) return;
+  const unsigned first = __ldg(job.intra_levels + level), end = __ldg(job.intra_levels + level + 1);
+  for (int i = threadIdx.x; i < 160; i += blockDim.x) lut[i] = c_bpred_lut[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned slot = first + blockIdx.x * kFlatWarps + warp;
+  if (slot >= end) return;
+  const unsigned mb_index = __ldg(job.intra_levels + job.n_intra_levels + 1 + slot);
+  const int r = mb_index / job.mb_cols, c = mb_index - r * job.mb_cols;
+  IntraMacroblock(job, r, c, lane, scratch[warp], lut, nullptr);
+}
+
+cudaError_t LaunchIntraFlat(const DevFrameJob *jobs, int n_frames, int level, int max_count, cudaStream_t st) {
+  if (max_count <= 0) return cudaSuccess;
+  dim3 grid((max_count + kFlatWarps - 1) / kFlatWarps, n_frames);
+  IntraFlatKernel<<<grid, kFlatWarps * 32, 0, st>>>(jobs, level);
+  return cudaGetLastError();
 }
 
 static size_t IntraSmemBytes(int max_rows) {
@@ -695,120 +728,265 @@ __device__ __forceinline__ void LfEdge(int *v, const LfLimits &lim, bool mb_edge
   }
 }
 
-// Extends the finished frame by kBorder replicated pixels on every side (8-byte granules: plane
-// widths are multiples of 8).
-__device__ void ExtendBorders(const DevFrameJob &job) {
+// Border extension: every plane of the finished frame gets kBorder replicated pixels on each side
+// (value = plane[clamp(y)][clamp(x)]), 8 bytes per thread-item, all items independent.
+__global__ void __launch_bounds__(256) BorderKernel(const DevFrameJob *__restrict__ jobs) {
+  const DevFrameJob &job = jobs[blockIdx.y];
   for (int pl = 0; pl < 3; ++pl) {
     uint8_t *base = pl == 0 ? job.cur.y : (pl == 1 ? job.cur.u : job.cur.v);
     const int pitch = pl == 0 ? job.pitch_y : job.pitch_c;
     const int w = job.mb_cols * (pl == 0 ? 16 : 8), h = job.mb_rows * (pl == 0 ? 16 : 8);
-    for (int t = threadIdx.x; t < h * 8; t += blockDim.x) {  // left / right, 8 bytes per item
-      const int row = t >> 3, part = t & 7;
-      uint8_t *rowp = base + (ptrdiff_t)row * pitch;
-      unsigned v = (part < 4 ? rowp[0] : rowp[w - 1]) * 0x01010101u;
-      uint8_t *d = part < 4 ? rowp - kBorder + 8 * part : rowp + w + 8 * (part - 4);
-      *reinterpret_cast<uint2 *>(d) = make_uint2(v, v);
-    }
-  }
-  __syncthreads();
-  for (int pl = 0; pl < 3; ++pl) {
-    uint8_t *base = pl == 0 ? job.cur.y : (pl == 1 ? job.cur.u : job.cur.v);
-    const int pitch = pl == 0 ? job.pitch_y : job.pitch_c;
-    const int w = job.mb_cols * (pl == 0 ? 16 : 8), h = job.mb_rows * (pl == 0 ? 16 : 8);
-    const int vecs = (w + 2 * kBorder) / 8;
-    for (int t = threadIdx.x; t < vecs * 2 * kBorder; t += blockDim.x) {  // top / bottom rows
-      const int k = t / vecs, x = t - k * vecs;
-      const int src_row = k < kBorder ? 0 : h - 1;
-      const int dst_row = k < kBorder ? k - kBorder : h + (k - kBorder);
-      const uint2 v = *reinterpret_cast<const uint2 *>(base + (ptrdiff_t)src_row * pitch - kBorder + 8 * x);
-      *reinterpret_cast<uint2 *>(base + (ptrdiff_t)dst_row * pitch - kBorder + 8 * x) = v;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(kWaveWarps * 32) FilterKernel(const DevFrameJob *__restrict__ jobs) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const DevFrameJob &job = jobs[blockIdx.x];
-  const int rows = job.mb_rows, cols = job.mb_cols;
-  volatile int *progress = reinterpret_cast<volatile int *>(smem_raw);
-  for (int i = threadIdx.x; i < rows; i += blockDim.x) progress[i] = 0;
-  __syncthreads();
-
-  if (job.lf_level != 0) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool simple = job.filter_type != 0;
-    const bool luma = lane < 16;
-    const int n = luma ? 16 : 8;
-    const int line = luma ? lane : (lane & 7);  // pixel row (vertical edges) / column (horizontal)
-    uint8_t *plane = luma ? job.cur.y : (lane < 24 ? job.cur.u : job.cur.v);
-    const int pitch = luma ? job.pitch_y : job.pitch_c;
-    const bool lane_on = luma || !simple;
-    const int n_edges = n / 4;
-
-    for (int r = warp; r < rows; r += kWaveWarps) {
-      for (int c = 0; c < cols; ++c) {
-        const unsigned flags = __ldg(&job.mbs[r * cols + c].flags);
-        const int level = (flags >> VP8R_MB_LF_SHIFT) & 63;
-        if (level) {
-          const bool inner = (flags & VP8R_MB_LF_INNER) != 0;
-          const LfLimits lim = MakeLimits(level, job.sharpness, job.key_frame != 0);
-          WaitRow(progress, r - 1, min(c + 2, cols));
-          uint8_t *mbp = plane + (ptrdiff_t)(r * n) * pitch + c * n;
-          if (lane_on) {
-            // ---- vertical edges: this lane owns pixel row `line`, columns -4 .. n-1 ----
-            unsigned *rowp = reinterpret_cast<unsigned *>(mbp + (ptrdiff_t)line * pitch - 4);
-            int v[20];
-#pragma unroll
-            for (int wd = 0; wd < 5; ++wd) {
-              if (wd <= n_edges) {
-                unsigned x = rowp[wd];
-                v[4 * wd] = x & 0xff; v[4 * wd + 1] = (x >> 8) & 0xff;
-                v[4 * wd + 2] = (x >> 16) & 0xff; v[4 * wd + 3] = x >> 24;
-              }
-            }
-            if (c > 0) LfEdge(v, lim, true, simple);
-            if (inner) {
-#pragma unroll
-              for (int e = 1; e < 4; ++e)
-                if (e < n_edges) LfEdge(v + 4 * e, lim, false, simple);
-            }
-#pragma unroll
-            for (int wd = 0; wd < 5; ++wd) {
-              if (wd <= n_edges && (wd > 0 || c > 0))
-                rowp[wd] = (unsigned)v[4 * wd] | ((unsigned)v[4 * wd + 1] << 8) | ((unsigned)v[4 * wd + 2] << 16) |
-                           ((unsigned)v[4 * wd + 3] << 24);
-            }
-          }
-          __syncwarp();
-          if (lane_on) {
-            // ---- horizontal edges: this lane owns pixel column `line`, rows -4 .. n-1 ----
-            uint8_t *colp = mbp + line;
-            int v[20];
-#pragma unroll
-            for (int y = 0; y < 20; ++y)
-              if (y < n + 4 && (y >= 4 || r > 0)) v[y] = colp[(ptrdiff_t)(y - 4) * pitch];
-            if (r > 0) LfEdge(v, lim, true, simple);
-            if (inner) {
-#pragma unroll
-              for (int e = 1; e < 4; ++e)
-                if (e < n_edges) LfEdge(v + 4 * e, lim, false, simple);
-            }
-#pragma unroll
-            for (int y = 1; y < 19; ++y)
-              if (y < n + 3 && (y >= 4 || r > 0)) colp[(ptrdiff_t)(y - 4) * pitch] = (uint8_t)v[y];
-          }
+    const int side_items = h * 8;                     // rows x (4 left + 4 right) granules
+    const int vecs = (w + 2 * kBorder) / 8;           // granules per full padded row
+    const int total = side_items + vecs * 2 * kBorder;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+      if (t < side_items) {
+        const int row = t >> 3, part = t & 7;
+        uint8_t *rowp = base + (ptrdiff_t)row * pitch;
+        const unsigned v = (part < 4 ? rowp[0] : rowp[w - 1]) * 0x01010101u;
+        uint8_t *d = part < 4 ? rowp - kBorder + 8 * part : rowp + w + 8 * (part - 4);
+        *reinterpret_cast<uint2 *>(d) = make_uint2(v, v);
+      } else {
+        const int u = t - side_items;
+        const int k = u / vecs, x8 = (u - k * vecs) * 8 - kBorder;  // destination x of the granule
+        const int src_row = k < kBorder ? 0 : h - 1;
+        const int dst_row = k < kBorder ? k - kBorder : h + (k - kBorder);
+        const uint8_t *srow = base + (ptrdiff_t)src_row * pitch;
+        uint2 v;
+        if (x8 < 0) {
+          const unsigned e = srow[0] * 0x01010101u;
+          v = make_uint2(e, e);
+        } else if (x8 >= w) {
+          const unsigned e = srow[w - 1] * 0x01010101u;
+          v = make_uint2(e, e);
+        } else {
+          v = *reinterpret_cast<const uint2 *>(srow + x8);
         }
-        PublishRow(progress, r, c + 1, lane);
+        *reinterpret_cast<uint2 *>(base + (ptrdiff_t)dst_row * pitch + x8) = v;
       }
     }
   }
-  __syncthreads();
-  ExtendBorders(job);
 }
 
-cudaError_t LaunchFilter(const DevFrameJob *jobs, int n_frames, int max_rows, cudaStream_t st) {
-  size_t smem = (size_t(max_rows) * 4 + 15) & ~size_t(15);
-  FilterKernel<<<n_frames, kWaveWarps * 32, smem, st>>>(jobs);
+// ---- loop-filter wavefront -------------------------------------------------------------------
+// A frame is cut into G horizontal bands of macroblock rows; one CTA per (frame, band), one warp
+// per macroblock row.  CTAs take a ticket at start (atomic counter) and tickets map to
+// (frame, band) with the bands of a frame in increasing order, so a CTA only ever waits for a CTA
+// holding a SMALLER ticket, i.e. one that is already running or done: no co-residency assumption.
+// Inside a band rows synchronise through shared-memory progress counters; the last row of a band
+// also publishes to global memory for the first row of the next band (another SM, so that row's
+// "above" pixels are read with ld.cg, past the non-coherent L1).
+constexpr int kFiltWarps = 8;
+constexpr int kMaxBands = 32;
+
+struct FiltTile {
+  unsigned y[16][5];   // own macroblock, luma rows (16 B used + 4 B pad: conflict-free row stores)
+  unsigned uv[2][8][3];  // U and V rows (8 B used + 4 B pad)
+};
+
+__device__ __forceinline__ int LoadFlagVolatile(const int *p) {
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+__global__ void __launch_bounds__(kFiltWarps * 32, 4) FilterKernel(const DevFrameJob *__restrict__ jobs, int n_bands,
+                                                                int *__restrict__ sync) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_ticket;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&sync[0], 1);
+  __syncthreads();
+  const int frame = s_ticket / n_bands, band = s_ticket - frame * n_bands;
+  const DevFrameJob &job = jobs[frame];
+  const int rows = job.mb_rows, cols = job.mb_cols;
+  const int rpb = (rows + n_bands - 1) / n_bands;
+  const int r0 = band * rpb, r1 = min(rows, r0 + rpb);
+  if (job.lf_level == 0 || r0 >= r1) return;
+  int *gflag = sync + 1 + frame * n_bands;  // gflag[b]: progress of the last row of band b
+  volatile int *lprog = reinterpret_cast<volatile int *>(smem_raw);
+  FiltTile *tiles = reinterpret_cast<FiltTile *>(smem_raw + ((rpb * 4 + 15) & ~15));
+  for (int i = threadIdx.x; i < rpb; i += blockDim.x) lprog[i] = 0;
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool simple = job.filter_type != 0;
+  const bool luma = lane < 16;
+  const int n = luma ? 16 : 8;
+  const int line = luma ? lane : (lane & 7);
+  uint8_t *plane = luma ? job.cur.y : (lane < 24 ? job.cur.u : job.cur.v);
+  const int pitch = luma ? job.pitch_y : job.pitch_c;
+  const bool lane_on = luma || !simple;
+  const int n_words = n / 4;  // own-macroblock words per pixel row
+  FiltTile &tile = tiles[warp];
+  unsigned *trow = luma ? tile.y[line] : tile.uv[lane < 24 ? 0 : 1][line];  // this lane's pixel row
+  unsigned char *tcol = luma ? reinterpret_cast<unsigned char *>(tile.y) + line
+                             : reinterpret_cast<unsigned char *>(tile.uv[lane < 24 ? 0 : 1]) + line;
+  const int tpitch = luma ? 20 : 12;  // bytes between tile rows
+
+  for (int lr = warp; lr < r1 - r0; lr += kFiltWarps) {
+    const int r = r0 + lr;
+    const bool last_of_band = (r == r1 - 1) && (band + 1 < n_bands);
+    uint8_t *rowp = plane + (ptrdiff_t)(r * n + line) * pitch;  // this lane's pixel row, x = 0
+    const vp8r_mb_info *mbrow = job.mbs + (size_t)r * cols;
+    // software pipeline: words and flags of macroblock c+1 are loaded while c is being filtered
+    unsigned nxt[4] = {0, 0, 0, 0};
+    unsigned nflags = __ldg(&mbrow[0].flags);
+    if (lane_on) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < n_words) nxt[k] = reinterpret_cast<const unsigned *>(rowp)[k];
+    }
+    unsigned carry = 0;  // columns n-4..n-1 of the previous macroblock of this pixel row
+
+    for (int c = 0; c < cols; ++c) {
+      unsigned cur[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
+      const unsigned flags = nflags;
+      if (c + 1 < cols) {
+        nflags = __ldg(&mbrow[c + 1].flags);
+        if (lane_on) {
+          const unsigned *np = reinterpret_cast<const unsigned *>(rowp + (c + 1) * n);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < n_words) nxt[k] = np[k];
+        }
+      }
+      const int level = (flags >> VP8R_MB_LF_SHIFT) & 63;
+      if (level == 0) {  // untouched: only hand the right-most columns to the next macroblock
+        carry = luma ? cur[3] : cur[1];
+        __syncwarp();
+        if (lane == 0) {
+          lprog[lr] = c + 1;
+          if (last_of_band) atomicExch(&gflag[band], c + 1);
+        }
+        continue;
+      }
+      const bool inner = (flags & VP8R_MB_LF_INNER) != 0;
+      const LfLimits lim = MakeLimits(level, job.sharpness, job.key_frame != 0);
+      const int need = min(c + 2, cols);
+      uint8_t *mbp = plane + (ptrdiff_t)(r * n) * pitch + c * n;
+
+      // Rows above: needed by the horizontal phase only.  If row r-1 is far enough already, start
+      // those loads now so they overlap the vertical phase; otherwise wait after it.
+      bool above_loaded = false;
+      int a4[4] = {0, 0, 0, 0};
+      if (r > 0) {
+        const int seen = lr > 0 ? lprog[lr - 1] : LoadFlagVolatile(&gflag[band - 1]);
+        if (seen >= need) {
+          if (lr > 0) __threadfence_block();
+          else __threadfence();
+          if (lane_on) {
+#pragma unroll
+            for (int y = 0; y < 4; ++y) a4[y] = __ldcg(mbp + line + (ptrdiff_t)(y - 4) * pitch);
+          }
+          above_loaded = true;
+        }
+      }
+
+      if (lane_on) {
+        // ---- vertical edges: lane = pixel row; v[0..3] = carry (previous MB), v[4..] = own ----
+        int v[20];
+        v[0] = carry & 0xff; v[1] = (carry >> 8) & 0xff; v[2] = (carry >> 16) & 0xff; v[3] = carry >> 24;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < n_words) {
+            v[4 + 4 * k] = cur[k] & 0xff; v[5 + 4 * k] = (cur[k] >> 8) & 0xff;
+            v[6 + 4 * k] = (cur[k] >> 16) & 0xff; v[7 + 4 * k] = cur[k] >> 24;
+          }
+        }
+        if (c > 0) LfEdge(v, lim, true, simple);
+        if (inner) {
+#pragma unroll
+          for (int e = 1; e < 4; ++e)
+            if (e < n_words) LfEdge(v + 4 * e, lim, false, simple);
+        }
+        if (c > 0)  // columns n-4..n-1 of the previous macroblock are final for this row now
+          *reinterpret_cast<unsigned *>(rowp + c * n - 4) =
+              (unsigned)v[0] | ((unsigned)v[1] << 8) | ((unsigned)v[2] << 16) | ((unsigned)v[3] << 24);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < n_words)
+            trow[k] = (unsigned)v[4 + 4 * k] | ((unsigned)v[5 + 4 * k] << 8) | ((unsigned)v[6 + 4 * k] << 16) |
+                      ((unsigned)v[7 + 4 * k] << 24);
+      }
+      __syncwarp();
+
+      if (r > 0 && !above_loaded) {
+        if (lr > 0) {
+          while (lprog[lr - 1] < need) __nanosleep(64);
+        } else {
+          while (LoadFlagVolatile(&gflag[band - 1]) < need) __nanosleep(128);
+        }
+        if (lr > 0) __threadfence_block();
+        else __threadfence();
+        if (lane_on) {
+#pragma unroll
+          for (int y = 0; y < 4; ++y) a4[y] = __ldcg(mbp + line + (ptrdiff_t)(y - 4) * pitch);
+        }
+      }
+
+      if (lane_on) {
+        // ---- horizontal edges: lane = pixel column; v[0..3] = rows above, v[4..] = own rows ----
+        int v[20];
+        v[0] = a4[0]; v[1] = a4[1]; v[2] = a4[2]; v[3] = a4[3];
+#pragma unroll
+        for (int y = 0; y < 16; ++y)
+          if (y < n) v[4 + y] = tcol[y * tpitch];
+        if (r > 0) LfEdge(v, lim, true, simple);
+        if (inner) {
+#pragma unroll
+          for (int e = 1; e < 4; ++e)
+            if (e < n_words) LfEdge(v + 4 * e, lim, false, simple);
+        }
+        if (r > 0) {
+#pragma unroll
+          for (int y = 1; y < 4; ++y) mbp[line + (ptrdiff_t)(y - 4) * pitch] = (uint8_t)v[y];
+        }
+#pragma unroll
+        for (int y = 0; y < 16; ++y)
+          if (y < n) tcol[y * tpitch] = (unsigned char)v[4 + y];
+      }
+      __syncwarp();
+      if (lane_on) {
+        // back to lane = pixel row: write the macroblock row out, keep its last word as carry
+        unsigned *outp = reinterpret_cast<unsigned *>(rowp + c * n);
+        if (luma) {
+          uint4 o = make_uint4(trow[0], trow[1], trow[2], trow[3]);
+          *reinterpret_cast<uint4 *>(outp) = o;
+          carry = o.w;
+        } else {
+          uint2 o = make_uint2(trow[0], trow[1]);
+          *reinterpret_cast<uint2 *>(outp) = o;
+          carry = o.y;
+        }
+      }
+      // every lane fences its own stores, then the warp agrees, then one lane publishes
+      if (last_of_band) __threadfence();
+      else __threadfence_block();
+      __syncwarp();
+      if (lane == 0) {
+        lprog[lr] = c + 1;
+        if (last_of_band) atomicExch(&gflag[band], c + 1);
+      }
+    }
+  }
+}
+
+cudaError_t LaunchFilter(const DevFrameJob *jobs, int n_frames, int max_rows, int *sync, int sync_ints,
+                         cudaStream_t st) {
+  // Bands: one warp per macroblock row (8-warp CTAs pack 4 per SM at 64 registers); with few frames
+  // in the batch, thinner bands put more SMs to work.
+  int n_bands = (max_rows + kFiltWarps - 1) / kFiltWarps;
+  while (n_bands < kMaxBands && n_frames * n_bands < 148 * 2 && (max_rows + n_bands) / (n_bands + 1) >= 3) ++n_bands;
+  if (n_bands > kMaxBands) n_bands = kMaxBands;
+  if (1 + n_frames * n_bands > sync_ints) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(sync, 0, sizeof(int) * (1 + (size_t)n_frames * n_bands), st);
+  if (e != cudaSuccess) return e;
+  const int rpb = (max_rows + n_bands - 1) / n_bands;
+  size_t smem = ((size_t(rpb) * 4 + 15) & ~size_t(15)) + sizeof(FiltTile) * kFiltWarps;
+  FilterKernel<<<n_frames * n_bands, kFiltWarps * 32, smem, st>>>(jobs, n_bands, sync);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  BorderKernel<<<dim3(8, n_frames), 256, 0, st>>>(jobs);
   return cudaGetLastError();
 }
 

@@ -27,6 +27,8 @@ struct DevFrameJob {
   int pitch_y, pitch_c;
   int mb_cols, mb_rows;
   int n_intra, n_inter;
+  int n_intra_levels;               // > 0: intra MBs are scheduled by dependency level (flat kernel)
+  const uint32_t *intra_levels;     // n_intra_levels+1 offsets, then MB indices sorted by level
   int16_t dq[4][6];
   uint8_t key_frame, version, filter_type, lf_level, sharpness;
   uint8_t pad[3];
@@ -42,8 +44,12 @@ cudaError_t InitKernelTables();
 cudaError_t LaunchInter(const DevFrameJob *jobs, int n_frames, int max_mbs, cudaStream_t st);
 // K_intra: dequant + IWHT/IDCT + intra prediction as a per-frame macroblock wavefront.
 cudaError_t LaunchIntra(const DevFrameJob *jobs, int n_frames, int max_rows, cudaStream_t st);
+// Flat intra: every intra MB of dependency level `level` (frames with n_intra_levels > 0).
+cudaError_t LaunchIntraFlat(const DevFrameJob *jobs, int n_frames, int level, int max_count, cudaStream_t st);
 // K_filter: normal/simple loop filter as a per-frame macroblock wavefront, then border extension.
-cudaError_t LaunchFilter(const DevFrameJob *jobs, int n_frames, int max_rows, cudaStream_t st);
+// `sync`: device scratch of `sync_ints` ints (ticket + one progress word per (frame, band)).
+cudaError_t LaunchFilter(const DevFrameJob *jobs, int n_frames, int max_rows, int *sync, int sync_ints,
+                         cudaStream_t st);
 // Device-side checksum of the cropped I420 image of each job's current surface.
 cudaError_t LaunchChecksum(const DevFrameJob *jobs, int n_frames, cudaStream_t st);
 

@@ -613,6 +613,59 @@ int FrameParser::ParseMacroblocks(vp8r_frame *out) {
   return VP8R_OK;
 }
 
+// Dependency levels of the intra macroblocks of an inter frame (see vp8r_frame_hdr.n_intra_levels).
+// Intra prediction reads the left, above-left, above and (B_PRED) above-right macroblocks; inter
+// neighbours are complete before any intra MB is touched, so only intra neighbours order the work.
+bool FrameParser::BuildIntraLevels(vp8r_frame *out) {
+  vp8r_frame_hdr &h = out->hdr;
+  const int cols = mb_cols_, rows = mb_rows_;
+  const size_t n_mb = size_t(cols) * rows;
+  const size_t n_intra = n_mb - h.n_inter_mbs;
+  h.n_intra_levels = 0;
+  h.intra_levels_at = 0;
+  if (n_intra == 0) return true;
+  levels_.assign(n_mb, 0);  // 0 = inter, k>0 = intra of level k-1
+  const vp8r_mb_info *mbs = out->mbs();
+  unsigned max_level = 0;
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) {
+      const size_t i = size_t(r) * cols + c;
+      if (mbs[i].flags & VP8R_MB_IS_INTER) continue;
+      unsigned lv = 0;
+      if (c > 0) lv = std::max<unsigned>(lv, levels_[i - 1]);
+      if (r > 0) {
+        lv = std::max<unsigned>(lv, levels_[i - cols]);
+        if (c > 0) lv = std::max<unsigned>(lv, levels_[i - cols - 1]);
+        if (c + 1 < cols) lv = std::max<unsigned>(lv, levels_[i - cols + 1]);
+      }
+      levels_[i] = uint16_t(lv + 1);
+      max_level = std::max(max_level, lv + 1);
+    }
+  if (max_level > kMaxFlatIntraLevels) return true;  // scheduled as a wavefront instead
+  // counting sort by level into the tail of the payload
+  const size_t table_bytes = (size_t(max_level) + 1 + n_intra) * 4;
+  const size_t blocks = (table_bytes + 31) / 32;
+  if (!EnsurePayload(out, size_t(h.n_payload_blocks) + blocks)) return false;
+  mbs = out->mbs();
+  uint32_t *tab = reinterpret_cast<uint32_t *>(out->payload() + size_t(h.n_payload_blocks) * 16);
+  std::memset(tab, 0, blocks * 32);
+  cursor_.assign(max_level, 0);
+  for (size_t i = 0; i < n_mb; ++i)
+    if (levels_[i]) cursor_[levels_[i] - 1]++;
+  tab[0] = 0;
+  for (unsigned k = 0; k < max_level; ++k) {
+    tab[k + 1] = tab[k] + cursor_[k];
+    cursor_[k] = tab[k];  // becomes the write cursor of level k
+  }
+  uint32_t *idx = tab + max_level + 1;
+  for (size_t i = 0; i < n_mb; ++i)
+    if (levels_[i]) idx[cursor_[levels_[i] - 1]++ ] = uint32_t(i);
+  h.n_intra_levels = max_level;
+  h.intra_levels_at = h.n_payload_blocks;
+  h.n_payload_blocks += uint32_t(blocks);
+  return true;
+}
+
 int FrameParser::Parse(const uint8_t *data, size_t size, vp8r_frame *out) {
   if (!data || !out) return Fail(VP8R_ERR_INVALID_ARG, "null argument");
   out->DropDeviceCopy();
@@ -657,6 +710,7 @@ int FrameParser::Parse(const uint8_t *data, size_t size, vp8r_frame *out) {
   rc = ParseMacroblocks(out);
   if (!refresh_entropy) probs_ = saved;
   if (rc != VP8R_OK) return rc;
+  if (!key_frame_ && !BuildIntraLevels(out)) return Fail(VP8R_ERR_NOMEM, "out of host memory");
 
   if (first_.Overrun()) return Fail(VP8R_ERR_TRUNCATED, "first partition read past its end");
   for (int i = 0; i < n_dct_parts_; ++i)

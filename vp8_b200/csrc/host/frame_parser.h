@@ -61,6 +61,8 @@ class FrameParser {
   int ReadCoefBlock(BoolReader &br, int type, int ctx, int first, int dc_f, int ac_f, int16_t *dst,
                     bool *nz_after_dequant);
   bool EnsurePayload(vp8r_frame *out, size_t blocks_needed);
+  bool BuildIntraLevels(vp8r_frame *out);
+  static constexpr unsigned kMaxFlatIntraLevels = 48;
 
   // ---- state that persists between frames (ParserContext, src/bitstream_parser.h:124-182) ----
   bool have_key_ = false;
@@ -89,6 +91,8 @@ class FrameParser {
   std::vector<Mv> sub_mvs_;           // 16 per MB (zero for intra MBs; src/decode.cc:71)
   std::vector<uint8_t> above_bmodes_; // 4 per MB column (key frames)
   std::vector<uint8_t> nz_above_y_, nz_above_u_, nz_above_v_, nz_above_y2_;  // per 4x4 column
+  std::vector<uint16_t> levels_;      // intra dependency level + 1 per MB (0 = inter)
+  std::vector<uint32_t> cursor_;
   std::string error_;
 };
 

@@ -94,6 +94,9 @@ struct vp8r_engine {
   bool own_stream = false;
   Slot slots[2];
   int cur_slot = 0;
+  // ticket + per-(frame, band) progress words of the wavefront kernels
+  int *d_sync = nullptr;
+  int sync_cap = 0;
   // checksum scratch
   DevFrameJob *h_cjobs = nullptr, *d_cjobs = nullptr;
   unsigned long long *d_sums = nullptr, *h_sums = nullptr;
@@ -312,6 +315,7 @@ VP8R_API void vp8r_engine_destroy(vp8r_engine *e) {
   if (e->d_cjobs) cudaFree(e->d_cjobs);
   if (e->h_sums) cudaFreeHost(e->h_sums);
   if (e->d_sums) cudaFree(e->d_sums);
+  if (e->d_sync) cudaFree(e->d_sync);
   for (auto &ev : e->fence_ev)
     if (ev) cudaEventDestroy(ev);
   DrainTimers(e);
@@ -408,7 +412,8 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
 
   // Pass 2: jobs + host->device staging.
   int max_mbs = 0, max_rows = 0;
-  bool any_inter = false, any_intra = false;
+  bool any_inter = false, any_intra = false, any_wave = false;
+  std::vector<int> level_max;  // per dependency level: most intra MBs of that level in any frame
   size_t at = 0;
   std::vector<int> cur_idx(n);
   {
@@ -439,6 +444,15 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
       const int n_mb = int(h.mb_cols) * h.mb_rows;
       j.n_inter = int(h.n_inter_mbs);
       j.n_intra = n_mb - j.n_inter;
+      j.n_intra_levels = int(h.n_intra_levels);
+      if (h.n_intra_levels) {
+        j.intra_levels = reinterpret_cast<const uint32_t *>(j.payload + size_t(h.intra_levels_at) * 16);
+        const uint32_t *tab = reinterpret_cast<const uint32_t *>(f->payload() + size_t(h.intra_levels_at) * 16);
+        if (level_max.size() < h.n_intra_levels) level_max.resize(h.n_intra_levels, 0);
+        for (uint32_t L = 0; L < h.n_intra_levels; ++L) level_max[L] = std::max(level_max[L], int(tab[L + 1] - tab[L]));
+      } else if (j.n_intra > 0) {
+        any_wave = true;
+      }
       std::memcpy(j.dq, h.dq, sizeof(j.dq));
       j.key_frame = h.key_frame;
       j.version = h.version;
@@ -463,12 +477,26 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
   }
   if (any_intra) {
     ScopedTimer t(e, 1);
-    CU_TRY(vp8r::LaunchIntra(sl.d_jobs, n, max_rows, e->st));
-    e->acc.launches_intra++;
+    for (size_t L = 0; L < level_max.size(); ++L) {
+      CU_TRY(vp8r::LaunchIntraFlat(sl.d_jobs, n, int(L), level_max[L], e->st));
+      e->acc.launches_intra++;
+    }
+    if (any_wave) {
+      CU_TRY(vp8r::LaunchIntra(sl.d_jobs, n, max_rows, e->st));
+      e->acc.launches_intra++;
+    }
   }
   {
     ScopedTimer t(e, 2);
-    CU_TRY(vp8r::LaunchFilter(sl.d_jobs, n, max_rows, e->st));
+    const int need_sync = 1 + n * 32;
+    if (need_sync > e->sync_cap) {
+      CU_TRY(cudaStreamSynchronize(e->st));
+      if (e->d_sync) cudaFree(e->d_sync);
+      e->d_sync = nullptr;
+      CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_sync), sizeof(int) * size_t(need_sync) * 2));
+      e->sync_cap = need_sync * 2;
+    }
+    CU_TRY(vp8r::LaunchFilter(sl.d_jobs, n, max_rows, e->d_sync, e->sync_cap, e->st));
     e->acc.launches_filter++;
   }
   CU_TRY(cudaEventRecord(sl.done, e->st));
