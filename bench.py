@@ -34,7 +34,7 @@ W, H, FRAMES = 1920, 1080, 30
 FRAME_BYTES = W * H * 3 // 2
 SYNTH = os.path.join(ROOT, "vp8_b200", "_lib", "vp8synth")
 REF_DECODE = os.path.join(ROOT, "oracle", "_ref", "decode")
-SYNTH_ARGS = "--width 1920 --height 1080 --frames 30 --log2-parts 2 --q 40 --lf 24 --pct-skip 45 --coef-density 4"
+SYNTH_ARGS = "--width 1920 --height 1080 --frames 30 --log2-parts 2 --q 40 --lf 24 --pct-skip 55 --coef-density 3 --pct-empty-block 80"
 
 
 def synth_stream(seed, path, frames=FRAMES):

@@ -153,6 +153,7 @@ struct Options {
   int segmentation = 1, lf_deltas = 1, golden_period = 7, altref_period = 11, hidden_altref = 1;
   int pct_intra = 8, pct_split = 10, pct_new = 30, pct_skip = 35, pct_bpred = 25;
   int coef_density = 6;  // expected non-zero coefficients per coded block (x2)
+  int pct_empty_block = 45;  // blocks without any coefficient inside a non-skipped macroblock
   std::string out = "synth.ivf";
 };
 
@@ -430,7 +431,7 @@ class Synth {
   // Sparse, low-frequency-weighted coefficients in zig-zag order; no int16 wrap after dequant.
   void MakeCoefs(int *z, int first, bool allow_dc, int amp) {
     std::memset(z, 0, sizeof(int) * 16);
-    if (Pct(45)) return;  // uncoded block
+    if (Pct(opt_.pct_empty_block)) return;  // uncoded block
     int n = 1 + int(rng_() % uint32_t(opt_.coef_density));
     for (int k = 0; k < n; ++k) {
       int pos = first + int((rng_() % 16) * (rng_() % 16) / 16);  // skewed to low frequencies
@@ -698,6 +699,7 @@ int main(int argc, char **argv) {
     else if (a == "--pct-skip") o.pct_skip = std::atoi(next());
     else if (a == "--pct-bpred") o.pct_bpred = std::atoi(next());
     else if (a == "--coef-density") o.coef_density = std::max(1, std::atoi(next()));
+    else if (a == "--pct-empty-block") o.pct_empty_block = std::atoi(next());
     else if (a == "--out") o.out = next();
     else {
       std::fprintf(stderr,
@@ -705,7 +707,7 @@ int main(int argc, char **argv) {
                    "       [--sharpness S] [--filter-type 0|1] [--version 0..3] [--log2-parts 0..3] [--segmentation 0|1]\n"
                    "       [--lf-deltas 0|1] [--golden-period N] [--altref-period N] [--hidden-altref 0|1]\n"
                    "       [--pct-intra P] [--pct-split P] [--pct-new P] [--pct-skip P] [--pct-bpred P]\n"
-                   "       [--coef-density N] --out file.ivf\n");
+                   "       [--coef-density N] [--pct-empty-block P] --out file.ivf\n");
       return 2;
     }
   }

@@ -2,16 +2,19 @@
 //
 // The reference (src/bool_decoder.cc:13-41) keeps a 16-bit window and renormalises one bit at a
 // time, pulling a byte every 8 shifts.  This reader produces the identical bit sequence with a
-// 64-bit left-aligned window that is refilled up to 7 bytes at a time and renormalised with one
-// count-leading-zeros per symbol.  `shifts_` counts renormalisation shifts so that the number of
-// bytes the reference's reader would have pulled (2 + shifts/8) can be compared with the
-// partition length: the reference throws std::out_of_range (src/utils.h:62-66) when it runs
-// past the end; we report VP8R_ERR_TRUNCATED for the same streams.
+// 64-bit left-aligned window: refills append up to 7 whole bytes with one big-endian 64-bit load,
+// the interval update is branch-free and renormalisation is one count-leading-zeros.
+//
+// Over-read detection: the reference's reader has consumed 2 + shifts/8 bytes after `shifts`
+// renormalisation shifts and throws std::out_of_range (src/utils.h:62-66) when that exceeds the
+// partition.  Here shifts == 8 * bytes_loaded - bits_available at any time, so nothing is counted
+// per symbol; Overrun() reports VP8R_ERR_TRUNCATED for the streams the reference would reject.
 #ifndef VP8R_HOST_BOOL_READER_H_
 #define VP8R_HOST_BOOL_READER_H_
 
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 
 namespace vp8r {
 
@@ -25,34 +28,29 @@ class BoolReader {
     size_ = size;
     window_ = 0;
     avail_ = 0;
+    loaded_ = 0;
     range_ = 255;
-    shifts_ = 0;
     used_ = false;
     Refill();
   }
 
+  // The reference initialises lazily (src/bool_decoder.cc:14-17): an unread partition never
+  // throws.  Callers mark a reader before its first symbol.
+  void MarkUsed() { used_ = true; }
+
   // One boolean with probability prob/256 of being 0.
   inline int Bit(int prob) {
-    uint32_t split = 1 + (((range_ - 1) * uint32_t(prob)) >> 8);
-    used_ = true;
-    if (avail_ < 8) Refill();
-    uint64_t big = uint64_t(split) << 56;
-    int bit;
-    if (window_ >= big) {
-      window_ -= big;
-      range_ -= split;
-      bit = 1;
-    } else {
-      range_ = split;
-      bit = 0;
-    }
-    // range_ is in [1,255]; bring it back to [128,255].
-    int sh = __builtin_clz(range_) - 24;
+    const uint32_t split = 1 + (((range_ - 1) * uint32_t(prob)) >> 8);
+    if (__builtin_expect(avail_ < 8, 0)) Refill();
+    const uint64_t big = uint64_t(split) << 56;
+    const uint64_t take = uint64_t(0) - uint64_t(window_ >= big);  // all ones when the bit is 1
+    window_ -= big & take;
+    range_ = split + ((range_ - 2 * split) & uint32_t(take));  // 1: range - split, 0: split
+    const int sh = __builtin_clz(range_) - 24;                 // back into [128, 255]
     range_ <<= sh;
     window_ <<= sh;
     avail_ -= sh;
-    shifts_ += uint32_t(sh);
-    return bit;
+    return int(take & 1);
   }
 
   inline int Bit128() { return Bit(128); }
@@ -74,29 +72,38 @@ class BoolReader {
   }
 
   // Bytes the reference's byte-at-a-time reader would have consumed so far.
-  size_t BytesConsumed() const { return 2 + size_t(shifts_ >> 3); }
-  // The reference initialises lazily (src/bool_decoder.cc:14-17): an unread partition never throws.
+  size_t BytesConsumed() const { return 2 + ((8 * loaded_ - size_t(avail_)) >> 3); }
   bool Overrun() const { return used_ && BytesConsumed() > size_; }
   size_t size() const { return size_; }
 
  private:
   inline void Refill() {
-    // Keep the window's top bits valid: append whole bytes below the `avail_` valid bits.
-    while (avail_ <= 56) {
-      uint64_t b = (cur_ < end_) ? uint64_t(*cur_) : 0;  // zeros past the end; Overrun() tells
-      if (cur_ < end_) ++cur_;
-      window_ |= b << (56 - avail_);
-      avail_ += 8;
+    const int k = (64 - avail_) >> 3;  // whole bytes that fit below the valid bits
+    if (end_ - cur_ >= 8) {
+      uint64_t w;
+      std::memcpy(&w, cur_, 8);
+      w = __builtin_bswap64(w);
+      // Bits of a partially fitting byte land below the counted ones; the next refill ORs the
+      // same values over them, so they are harmless.
+      window_ |= avail_ ? (w >> avail_) : w;
+      cur_ += k;
+    } else {
+      for (int i = 0; i < k; ++i) {
+        const uint64_t b = cur_ < end_ ? uint64_t(*cur_++) : 0;  // zeros past the end; Overrun() tells
+        window_ |= b << (56 - avail_ - 8 * i);
+      }
     }
+    avail_ += 8 * k;
+    loaded_ += size_t(k);
   }
 
   const uint8_t *cur_ = nullptr;
   const uint8_t *end_ = nullptr;
   size_t size_ = 0;
   uint64_t window_ = 0;  // next bits of the stream, left aligned
-  int avail_ = 0;        // number of valid bits in window_
+  int avail_ = 0;        // number of counted valid bits in window_
+  size_t loaded_ = 0;    // bytes appended so far (virtual zeros past the end included)
   uint32_t range_ = 255;
-  uint32_t shifts_ = 0;
   bool used_ = false;
 };
 

@@ -146,6 +146,7 @@ int FrameParser::ParseHeader(const uint8_t *data, size_t size, vp8r_frame *out) 
   // The reference's SubSpan needs at least one byte after the first partition (src/utils.h:78-83).
   if (tag_size + first_size >= size) return Fail(VP8R_ERR_TRUNCATED, "first partition exceeds the frame");
   first_.Init(data + tag_size, first_size);
+  first_.MarkUsed();
   BoolReader &br = first_;
 
   if (key_frame_) {
@@ -258,7 +259,8 @@ int16_t FrameParser::ReadMvComponent(const uint8_t *p) {  // bitstream_parser.cc
 }
 
 // One 4x4 block of tokens (bitstream_parser.cc:572-621).  Coefficients are written de-zigzagged
-// into dst[16] (pre-zeroed by the caller).  Returns 1 when any coefficient is non-zero.
+// into dst[16] (zeroed here once the block is known to be non-empty).  Returns 1 when any
+// coefficient is non-zero (a block of explicit zero tokens returns 0 and leaves zeros in dst).
 // *nz_after_dequant mirrors what the reference later derives from the DEQUANTISED int16 values
 // (decode_frame.cc:6-47): a product that wraps to 0 in int16 counts as zero there.
 int FrameParser::ReadCoefBlock(BoolReader &br, int type, int ctx, int first, int dc_f, int ac_f,
@@ -268,8 +270,17 @@ int FrameParser::ReadCoefBlock(BoolReader &br, int type, int ctx, int first, int
   const uint8_t *p = bands[kBand[n]][ctx];
   int any = 0;
   bool dq_any = false;
+  // Most blocks are empty: their first symbol is the end-of-block branch.  Decide that before
+  // touching the destination.
+  if (!br.Bit(p[0])) {
+    *nz_after_dequant = false;
+    return 0;
+  }
+  std::memset(dst, 0, 32);
+  bool first_symbol = true;
   while (n < 16) {
-    if (!br.Bit(p[0])) break;  // end of block (not coded right after a zero token)
+    if (!first_symbol && !br.Bit(p[0])) break;  // end of block (not coded right after a zero token)
+    first_symbol = false;
     while (!br.Bit(p[1])) {    // zero token(s)
       if (++n == 16) goto done;
       p = bands[kBand[n]][0];
@@ -518,13 +529,13 @@ int FrameParser::ParseMacroblocks(vp8r_frame *out) {
       uint32_t mask = 0;
       mb->coef_offset = h.n_payload_blocks;
       if (!skip) {
+        tok.MarkUsed();
         int16_t *dst = out->payload() + size_t(h.n_payload_blocks) * 16;
         uint32_t stored = 0;
         bool dqnz;
         uint32_t raw = 0;  // raw non-zero flags, bit b as in coef_mask
         uint32_t dqf = 0;  // non-zero after dequantisation
         if (has_y2) {
-          std::memset(dst, 0, 32);
           int ctx = nz_above_y2_[c] + nz_left_y2;
           if (ReadCoefBlock(tok, 1, ctx, 0, dq[VP8R_DQ_Y2_DC], dq[VP8R_DQ_Y2_AC], dst, &dqnz)) {
             raw |= 1;
@@ -538,7 +549,6 @@ int FrameParser::ParseMacroblocks(vp8r_frame *out) {
           int i = b >> 2, j = b & 3;
           int a = i ? int((raw >> (b - 3)) & 1) : nz_above_y_[c * 4 + j];  // block b-4 is bit b-3
           int l = j ? int((raw >> b) & 1) : nz_left_y[i];                  // block b-1 is bit b
-          std::memset(dst, 0, 32);
           if (ReadCoefBlock(tok, ytype, a + l, yfirst, dq[VP8R_DQ_Y1_DC], dq[VP8R_DQ_Y1_AC], dst, &dqnz)) {
             raw |= 2u << b;
             dst += 16;
@@ -554,7 +564,6 @@ int FrameParser::ParseMacroblocks(vp8r_frame *out) {
             int i = b >> 1, j = b & 1;
             int a = i ? int((raw >> (base + b - 2)) & 1) : na[j];
             int l = j ? int((raw >> (base + b - 1)) & 1) : nl[i];
-            std::memset(dst, 0, 32);
             if (ReadCoefBlock(tok, 2, a + l, 0, dq[VP8R_DQ_UV_DC], dq[VP8R_DQ_UV_AC], dst, &dqnz)) {
               raw |= 1u << (base + b);
               dst += 16;
