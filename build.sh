@@ -14,9 +14,8 @@ g++ $CXXFLAGS -march=x86-64-v3 -fPIC -fvisibility=hidden -Wall -Wextra -c vp8_b2
 g++ $CXXFLAGS -fPIC -fvisibility=hidden -Wall -Wextra -c vp8_b200/csrc/capi.cc -o vp8_b200/_build/capi.o
 $NVCC $ARCH -shared -o "$OUT/libvp8r.so" vp8_b200/_build/recon_kernels.o vp8_b200/_build/engine.o \
     vp8_b200/_build/frame_parser.o vp8_b200/_build/capi.o -lpthread
-if [ -f tools/vp8synth.cc ]; then
-  g++ -O2 -std=c++17 -Wall -Wextra tools/vp8synth.cc -o "$OUT/vp8synth"
-fi
+g++ -O2 -std=c++17 -Wall -Wextra tools/vp8synth.cc -o "$OUT/vp8synth"
+g++ -O2 -std=c++17 -Wall -Wextra -Iinclude tools/vp8dec.cc -o "$OUT/vp8dec" -L"$OUT" -lvp8r -Wl,-rpath,'$ORIGIN'
 make -s -C oracle oracle
 if [ "${SKIP_REF:-0}" != "1" ]; then make -s -C oracle ref; fi
 echo "built $OUT/libvp8r.so"
