@@ -682,49 +682,52 @@ __device__ __forceinline__ LfLimits MakeLimits(int level, int sharp, bool key) {
   return l;
 }
 
-// src/filter.cc:22-35
-__device__ __forceinline__ void LfAdjust(int &p1, int &p0, int &q0, int &q1, bool outer) {
-  int a = clamp128((outer ? clamp128(p1 - q1) : 0) + 3 * (q0 - p0));
-  int f1 = min(a + 4, 127) >> 3, f2 = min(a + 3, 127) >> 3;
-  p0 = clamp255(p0 + f2);
-  q0 = clamp255(q0 - f1);
-  if (!outer) {
-    a = (f1 + 1) >> 1;
-    p1 = clamp255(p1 + a);
-    q1 = clamp255(q1 - a);
-  }
-}
+// One edge on 8 pixels v[0..7] = p3 p2 p1 p0 | q0 q1 q2 q3, branch-free: every lane evaluates the
+// mask, the high-variance test and both filter variants and selects per-pixel deltas (a warp's 32
+// lines almost always disagree on the tests, so branching would execute every path anyway).
+//   mask / hev:      src/filter.cc:7-20      Adjust:            src/filter.cc:22-35
+//   sub-block edge:  src/filter.cc:37-44     macroblock edge:   src/filter.cc:46-67
+//   simple filter:   src/filter.cc:14-16,69-71 (luma only)
+__device__ __forceinline__ int AddClamp255(int p, int d) { return min(max(p + d, 0), 255); }
 
-// One edge on 8 pixels v[0..7] = p3 p2 p1 p0 | q0 q1 q2 q3.  kind: 0 macroblock edge, 1 sub-block
-// edge (src/filter.cc:37-67); simple = luma-only simple filter (src/filter.cc:14-16,69-71).
-__device__ __forceinline__ void LfEdge(int *v, const LfLimits &lim, bool mb_edge, bool simple) {
-  const int edge = mb_edge ? lim.edge_mb : lim.edge_sb;
-  int &p3 = v[0], &p2 = v[1], &p1 = v[2], &p0 = v[3], &q0 = v[4], &q1 = v[5], &q2 = v[6], &q3 = v[7];
-  if (abs(p0 - q0) * 2 + (abs(p1 - q1) >> 1) > edge) return;
+template <bool kMbEdge>
+__device__ __forceinline__ void LfEdge(int *v, const LfLimits &lim, bool simple) {
+  const int edge = kMbEdge ? lim.edge_mb : lim.edge_sb;
+  const int p3 = v[0], p2 = v[1], p1 = v[2], p0 = v[3], q0 = v[4], q1 = v[5], q2 = v[6], q3 = v[7];
+  const int d_p1q1 = p1 - q1, d_q0p0 = q0 - p0;
+  const bool edge_ok = abs(d_q0p0) * 2 + (abs(d_p1q1) >> 1) <= edge;
+  const int s = clamp128(d_p1q1);
   if (simple) {
-    LfAdjust(p1, p0, q0, q1, true);
+    const int a = clamp128(s + 3 * d_q0p0);
+    const int f1 = min(a + 4, 127) >> 3, f2 = min(a + 3, 127) >> 3;
+    v[3] = AddClamp255(p0, edge_ok ? f2 : 0);
+    v[4] = AddClamp255(q0, edge_ok ? -f1 : 0);
     return;
   }
-  const int I = lim.interior;
-  if (abs(p3 - p2) > I || abs(p2 - p1) > I || abs(p1 - p0) > I || abs(q0 - q1) > I || abs(q1 - q2) > I ||
-      abs(q2 - q3) > I)
-    return;
-  const bool hev = abs(p1 - p0) > lim.hev || abs(q1 - q0) > lim.hev;
-  if (!mb_edge) {
-    LfAdjust(p1, p0, q0, q1, hev);
-  } else if (hev) {
-    LfAdjust(p1, p0, q0, q1, true);
+  const int a_p1p0 = abs(p1 - p0), a_q1q0 = abs(q1 - q0);
+  const int interior = max(max(max(abs(p3 - p2), abs(p2 - p1)), a_p1p0), max(max(a_q1q0, abs(q1 - q2)), abs(q2 - q3)));
+  const bool on = edge_ok && interior <= lim.interior;
+  const bool hev = max(a_p1p0, a_q1q0) > lim.hev;
+  if (kMbEdge) {
+    const int w = clamp128(s + 3 * d_q0p0);
+    const int f1 = min(w + 4, 127) >> 3, f2 = min(w + 3, 127) >> 3;  // hev: Adjust(true)
+    const int a27 = (27 * w + 63) >> 7, a18 = (18 * w + 63) >> 7, a9 = (9 * w + 63) >> 7;
+    const int dp0 = on ? (hev ? f2 : a27) : 0, dq0 = on ? (hev ? f1 : a27) : 0;
+    const int d1 = (on && !hev) ? a18 : 0, d2 = (on && !hev) ? a9 : 0;
+    v[1] = AddClamp255(p2, d2);
+    v[2] = AddClamp255(p1, d1);
+    v[3] = AddClamp255(p0, dp0);
+    v[4] = AddClamp255(q0, -dq0);
+    v[5] = AddClamp255(q1, -d1);
+    v[6] = AddClamp255(q2, -d2);
   } else {
-    int w = clamp128(clamp128(p1 - q1) + 3 * (q0 - p0));
-    int a = (27 * w + 63) >> 7;
-    q0 = clamp255(q0 - a);
-    p0 = clamp255(p0 + a);
-    a = (18 * w + 63) >> 7;
-    q1 = clamp255(q1 - a);
-    p1 = clamp255(p1 + a);
-    a = (9 * w + 63) >> 7;
-    q2 = clamp255(q2 - a);
-    p2 = clamp255(p2 + a);
+    const int a = clamp128((hev ? s : 0) + 3 * d_q0p0);  // Adjust(hev)
+    const int f1 = min(a + 4, 127) >> 3, f2 = min(a + 3, 127) >> 3;
+    const int a2 = (on && !hev) ? ((f1 + 1) >> 1) : 0;
+    v[2] = AddClamp255(p1, a2);
+    v[3] = AddClamp255(p0, on ? f2 : 0);
+    v[4] = AddClamp255(q0, on ? -f1 : 0);
+    v[5] = AddClamp255(q1, -a2);
   }
 }
 
@@ -778,20 +781,21 @@ __global__ void __launch_bounds__(256) BorderKernel(const DevFrameJob *__restric
 // "above" pixels are read with ld.cg, past the non-coherent L1).
 constexpr int kFiltWarps = 8;
 constexpr int kMaxBands = 32;
+constexpr int kBandStride = 8;  // macroblocks between cross-SM progress publications
 
-struct FiltTile {
-  unsigned y[16][5];   // own macroblock, luma rows (16 B used + 4 B pad: conflict-free row stores)
-  unsigned uv[2][8][3];  // U and V rows (8 B used + 4 B pad)
+struct __align__(16) FiltTile {
+  unsigned char bytes[16 * 20 + 2 * 8 * 12];  // luma rows of 16 B (+4 pad: conflict-free row
+                                              // stores), then U and V rows of 8 B (+4 pad)
 };
 
-__device__ __forceinline__ int LoadFlagVolatile(const int *p) {
+__device__ __forceinline__ int LoadFlagAcquire(const int *p) {
   int v;
-  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
 __global__ void __launch_bounds__(kFiltWarps * 32, 4) FilterKernel(const DevFrameJob *__restrict__ jobs, int n_bands,
-                                                                int *__restrict__ sync) {
+                                                                   int *__restrict__ sync) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_ticket;
   if (threadIdx.x == 0) s_ticket = atomicAdd(&sync[0], 1);
@@ -802,14 +806,19 @@ __global__ void __launch_bounds__(kFiltWarps * 32, 4) FilterKernel(const DevFram
   const int rpb = (rows + n_bands - 1) / n_bands;
   const int r0 = band * rpb, r1 = min(rows, r0 + rpb);
   if (job.lf_level == 0 || r0 >= r1) return;
-  int *gflag = sync + 1 + frame * n_bands;  // gflag[b]: progress of the last row of band b
+  int *gflag = sync + 1 + frame * n_bands;  // gflag[b]: macroblocks < gflag[b] of band b's last row are final
   volatile int *lprog = reinterpret_cast<volatile int *>(smem_raw);
   FiltTile *tiles = reinterpret_cast<FiltTile *>(smem_raw + ((rpb * 4 + 15) & ~15));
   for (int i = threadIdx.x; i < rpb; i += blockDim.x) lprog[i] = 0;
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Everything read from the job is copied to registers here: the pixel stores below are char-typed
+  // and would otherwise force the compiler to reload job fields from global memory after each one.
   const bool simple = job.filter_type != 0;
+  const int sharpness = job.sharpness;
+  const bool key_frame = job.key_frame != 0;
+  const vp8r_mb_info *const mbs = job.mbs;
   const bool luma = lane < 16;
   const int n = luma ? 16 : 8;
   const int line = luma ? lane : (lane & 7);
@@ -817,26 +826,38 @@ __global__ void __launch_bounds__(kFiltWarps * 32, 4) FilterKernel(const DevFram
   const int pitch = luma ? job.pitch_y : job.pitch_c;
   const bool lane_on = luma || !simple;
   const int n_words = n / 4;  // own-macroblock words per pixel row
-  FiltTile &tile = tiles[warp];
-  unsigned *trow = luma ? tile.y[line] : tile.uv[lane < 24 ? 0 : 1][line];  // this lane's pixel row
-  unsigned char *tcol = luma ? reinterpret_cast<unsigned char *>(tile.y) + line
-                             : reinterpret_cast<unsigned char *>(tile.uv[lane < 24 ? 0 : 1]) + line;
+  // Transposition tile of this warp, addressed by integer offsets from the dynamic shared-memory
+  // base so that every access stays an LDS/STS (no generic addressing).
+  unsigned char *const tb = reinterpret_cast<unsigned char *>(tiles + warp);
   const int tpitch = luma ? 20 : 12;  // bytes between tile rows
+  const int tbase = luma ? 0 : 320 + (lane < 24 ? 0 : 96);
+  const int trow_off = tbase + line * tpitch;  // this lane's pixel row
+  const int tcol_off = tbase + line;           // this lane's pixel column
 
   for (int lr = warp; lr < r1 - r0; lr += kFiltWarps) {
     const int r = r0 + lr;
     const bool last_of_band = (r == r1 - 1) && (band + 1 < n_bands);
+    const bool has_above = r > 0;
+    const bool above_local = lr > 0;  // the row above is in this CTA (shared flag) or on another SM
     uint8_t *rowp = plane + (ptrdiff_t)(r * n + line) * pitch;  // this lane's pixel row, x = 0
-    const vp8r_mb_info *mbrow = job.mbs + (size_t)r * cols;
+    const uint8_t *abovep = plane + (ptrdiff_t)(r * n - 4) * pitch + line;  // column `line`, 4 rows up
+    const vp8r_mb_info *mbrow = mbs + (size_t)r * cols;
     // software pipeline: words and flags of macroblock c+1 are loaded while c is being filtered
     unsigned nxt[4] = {0, 0, 0, 0};
     unsigned nflags = __ldg(&mbrow[0].flags);
     if (lane_on) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (k < n_words) nxt[k] = reinterpret_cast<const unsigned *>(rowp)[k];
+      if (luma) {
+        const uint4 t = *reinterpret_cast<const uint4 *>(rowp);
+        nxt[0] = t.x; nxt[1] = t.y; nxt[2] = t.z; nxt[3] = t.w;
+      } else {
+        const uint2 t = *reinterpret_cast<const uint2 *>(rowp);
+        nxt[0] = t.x; nxt[1] = t.y;
+      }
     }
-    unsigned carry = 0;  // columns n-4..n-1 of the previous macroblock of this pixel row
+    unsigned carry = 0;    // columns n-4..n-1 of the previous macroblock of this pixel row
+    int a4n[4] = {0, 0, 0, 0};  // rows above of macroblock c, prefetched during c-1 when allowed
+    int gseen = 0;              // last value read from the band above's global progress word
+    bool have_above = false;
 
     for (int c = 0; c < cols; ++c) {
       unsigned cur[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
@@ -844,129 +865,146 @@ __global__ void __launch_bounds__(kFiltWarps * 32, 4) FilterKernel(const DevFram
       if (c + 1 < cols) {
         nflags = __ldg(&mbrow[c + 1].flags);
         if (lane_on) {
-          const unsigned *np = reinterpret_cast<const unsigned *>(rowp + (c + 1) * n);
+          const uint8_t *np = rowp + (c + 1) * n;
+          if (luma) {
+            const uint4 t = *reinterpret_cast<const uint4 *>(np);
+            nxt[0] = t.x; nxt[1] = t.y; nxt[2] = t.z; nxt[3] = t.w;
+          } else {
+            const uint2 t = *reinterpret_cast<const uint2 *>(np);
+            nxt[0] = t.x; nxt[1] = t.y;
+          }
+        }
+      }
+      // Non-blocking sample of the progress of the row above; consumed at the end of the
+      // iteration to decide whether the next macroblock's rows above can be fetched early.
+      int seen = 0;
+      if (has_above) seen = above_local ? lprog[lr - 1] : gseen;  // cross-SM progress: cached, see below
+
+      const int level = (flags >> VP8R_MB_LF_SHIFT) & 63;
+      if (level != 0) {
+        const bool inner = (flags & VP8R_MB_LF_INNER) != 0;
+        const LfLimits lim = MakeLimits(level, sharpness, key_frame);
+        const int need = min(c + 2, cols);
+        uint8_t *mbp = plane + (ptrdiff_t)(r * n) * pitch + c * n;
+
+        if (lane_on) {
+          // ---- vertical edges: lane = pixel row; v[0..3] = carry (previous MB), v[4..] = own ----
+          int v[20];
+          v[0] = carry & 0xff; v[1] = (carry >> 8) & 0xff; v[2] = (carry >> 16) & 0xff; v[3] = carry >> 24;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < n_words) {
+              v[4 + 4 * k] = cur[k] & 0xff; v[5 + 4 * k] = (cur[k] >> 8) & 0xff;
+              v[6 + 4 * k] = (cur[k] >> 16) & 0xff; v[7 + 4 * k] = cur[k] >> 24;
+            }
+          }
+          if (c > 0) LfEdge<true>(v, lim, simple);
+          if (inner) {
+#pragma unroll
+            for (int e = 1; e < 4; ++e)
+              if (e < n_words) LfEdge<false>(v + 4 * e, lim, simple);
+          }
+          if (c > 0)  // columns n-4..n-1 of the previous macroblock are final for this row now
+            *reinterpret_cast<unsigned *>(rowp + c * n - 4) =
+                (unsigned)v[0] | ((unsigned)v[1] << 8) | ((unsigned)v[2] << 16) | ((unsigned)v[3] << 24);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (k < n_words) nxt[k] = np[k];
+            if (k < n_words)
+              *reinterpret_cast<unsigned *>(tb + trow_off + 4 * k) =
+                  (unsigned)v[4 + 4 * k] | ((unsigned)v[5 + 4 * k] << 8) | ((unsigned)v[6 + 4 * k] << 16) |
+                  ((unsigned)v[7 + 4 * k] << 24);
         }
-      }
-      const int level = (flags >> VP8R_MB_LF_SHIFT) & 63;
-      if (level == 0) {  // untouched: only hand the right-most columns to the next macroblock
-        carry = luma ? cur[3] : cur[1];
         __syncwarp();
-        if (lane == 0) {
-          lprog[lr] = c + 1;
-          if (last_of_band) atomicExch(&gflag[band], c + 1);
-        }
-        continue;
-      }
-      const bool inner = (flags & VP8R_MB_LF_INNER) != 0;
-      const LfLimits lim = MakeLimits(level, job.sharpness, job.key_frame != 0);
-      const int need = min(c + 2, cols);
-      uint8_t *mbp = plane + (ptrdiff_t)(r * n) * pitch + c * n;
 
-      // Rows above: needed by the horizontal phase only.  If row r-1 is far enough already, start
-      // those loads now so they overlap the vertical phase; otherwise wait after it.
-      bool above_loaded = false;
-      int a4[4] = {0, 0, 0, 0};
-      if (r > 0) {
-        const int seen = lr > 0 ? lprog[lr - 1] : LoadFlagVolatile(&gflag[band - 1]);
-        if (seen >= need) {
-          if (lr > 0) __threadfence_block();
-          else __threadfence();
+        int a4[4] = {a4n[0], a4n[1], a4n[2], a4n[3]};
+        if (has_above && !have_above) {  // not prefetched: wait for the row above, then fetch
+          // back off in proportion to how far behind the row above still is (>= ~1 us per
+          // macroblock), so rows that cannot start yet do not eat issue slots polling
+          if (above_local) {
+            for (int got = lprog[lr - 1]; got < need; got = lprog[lr - 1]) __nanosleep(min(250 + 700 * (need - got - 1), 20000));
+            __threadfence_block();
+          } else {
+            // The band above publishes in strides of kBandStride macroblocks, so one successful
+            // poll usually covers the next several macroblocks (and their prefetches).
+            for (gseen = LoadFlagAcquire(&gflag[band - 1]); gseen < need; gseen = LoadFlagAcquire(&gflag[band - 1]))
+              __nanosleep(min(200 + 600 * (need - gseen - 1), 20000));
+          }
           if (lane_on) {
 #pragma unroll
-            for (int y = 0; y < 4; ++y) a4[y] = __ldcg(mbp + line + (ptrdiff_t)(y - 4) * pitch);
-          }
-          above_loaded = true;
-        }
-      }
-
-      if (lane_on) {
-        // ---- vertical edges: lane = pixel row; v[0..3] = carry (previous MB), v[4..] = own ----
-        int v[20];
-        v[0] = carry & 0xff; v[1] = (carry >> 8) & 0xff; v[2] = (carry >> 16) & 0xff; v[3] = carry >> 24;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (k < n_words) {
-            v[4 + 4 * k] = cur[k] & 0xff; v[5 + 4 * k] = (cur[k] >> 8) & 0xff;
-            v[6 + 4 * k] = (cur[k] >> 16) & 0xff; v[7 + 4 * k] = cur[k] >> 24;
+            for (int y = 0; y < 4; ++y) a4[y] = __ldcg(abovep + c * n + (ptrdiff_t)y * pitch);
           }
         }
-        if (c > 0) LfEdge(v, lim, true, simple);
-        if (inner) {
+        if (lane_on) {
+          // ---- horizontal edges: lane = pixel column; v[0..3] = rows above, v[4..] = own rows ----
+          int v[20];
+          v[0] = a4[0]; v[1] = a4[1]; v[2] = a4[2]; v[3] = a4[3];
 #pragma unroll
-          for (int e = 1; e < 4; ++e)
-            if (e < n_words) LfEdge(v + 4 * e, lim, false, simple);
+          for (int y = 0; y < 16; ++y)
+            if (y < n) v[4 + y] = tb[tcol_off + y * tpitch];
+          if (has_above) LfEdge<true>(v, lim, simple);
+          if (inner) {
+#pragma unroll
+            for (int e = 1; e < 4; ++e)
+              if (e < n_words) LfEdge<false>(v + 4 * e, lim, simple);
+          }
+          if (has_above) {
+#pragma unroll
+            for (int y = 1; y < 4; ++y) mbp[line + (ptrdiff_t)(y - 4) * pitch] = (uint8_t)v[y];
+          }
+#pragma unroll
+          for (int y = 0; y < 16; ++y)
+            if (y < n) tb[tcol_off + y * tpitch] = (unsigned char)v[4 + y];
         }
-        if (c > 0)  // columns n-4..n-1 of the previous macroblock are final for this row now
-          *reinterpret_cast<unsigned *>(rowp + c * n - 4) =
-              (unsigned)v[0] | ((unsigned)v[1] << 8) | ((unsigned)v[2] << 16) | ((unsigned)v[3] << 24);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < n_words)
-            trow[k] = (unsigned)v[4 + 4 * k] | ((unsigned)v[5 + 4 * k] << 8) | ((unsigned)v[6 + 4 * k] << 16) |
-                      ((unsigned)v[7 + 4 * k] << 24);
+        __syncwarp();
+        if (lane_on) {
+          // back to lane = pixel row: write the macroblock row out, keep its last word as carry
+          unsigned *outp = reinterpret_cast<unsigned *>(rowp + c * n);
+          const unsigned *tr = reinterpret_cast<const unsigned *>(tb + trow_off);
+          if (luma) {
+            uint4 o = make_uint4(tr[0], tr[1], tr[2], tr[3]);
+            *reinterpret_cast<uint4 *>(outp) = o;
+            carry = o.w;
+          } else {
+            uint2 o = make_uint2(tr[0], tr[1]);
+            *reinterpret_cast<uint2 *>(outp) = o;
+            carry = o.y;
+          }
+        }
+      } else {
+        carry = luma ? cur[3] : cur[1];  // untouched macroblock: just hand its last columns on
       }
-      __syncwarp();
 
-      if (r > 0 && !above_loaded) {
-        if (lr > 0) {
-          while (lprog[lr - 1] < need) __nanosleep(64);
-        } else {
-          while (LoadFlagVolatile(&gflag[band - 1]) < need) __nanosleep(128);
-        }
-        if (lr > 0) __threadfence_block();
-        else __threadfence();
+      // Rows above of the next macroblock: fetch now if the row above is already far enough, so
+      // the loads overlap the next vertical phase (a row that runs too close behind its
+      // predecessor waits above, drops back, and from then on always finds them ready).
+      have_above = false;
+      if (has_above && c + 1 < cols && seen >= min(c + 3, cols)) {
+        if (above_local) __threadfence_block();
         if (lane_on) {
 #pragma unroll
-          for (int y = 0; y < 4; ++y) a4[y] = __ldcg(mbp + line + (ptrdiff_t)(y - 4) * pitch);
+          for (int y = 0; y < 4; ++y) a4n[y] = __ldcg(abovep + (c + 1) * n + (ptrdiff_t)y * pitch);
         }
+        have_above = true;
       }
 
-      if (lane_on) {
-        // ---- horizontal edges: lane = pixel column; v[0..3] = rows above, v[4..] = own rows ----
-        int v[20];
-        v[0] = a4[0]; v[1] = a4[1]; v[2] = a4[2]; v[3] = a4[3];
-#pragma unroll
-        for (int y = 0; y < 16; ++y)
-          if (y < n) v[4 + y] = tcol[y * tpitch];
-        if (r > 0) LfEdge(v, lim, true, simple);
-        if (inner) {
-#pragma unroll
-          for (int e = 1; e < 4; ++e)
-            if (e < n_words) LfEdge(v + 4 * e, lim, false, simple);
-        }
-        if (r > 0) {
-#pragma unroll
-          for (int y = 1; y < 4; ++y) mbp[line + (ptrdiff_t)(y - 4) * pitch] = (uint8_t)v[y];
-        }
-#pragma unroll
-        for (int y = 0; y < 16; ++y)
-          if (y < n) tcol[y * tpitch] = (unsigned char)v[4 + y];
+      // Publish.  Same-CTA consumers: block-scope fence, shared flag, every macroblock.  The next
+      // band (another SM) needs a device-scope fence, which costs ~2.5k cycles when stores are in
+      // flight: it is paid once per kBandStride macroblocks, otherwise the last row of every band
+      // would run at less than half the speed of the others and throttle all rows below it.
+      if (last_of_band && (c % kBandStride) == kBandStride - 1) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicExch(&gflag[band], c + 1);  // macroblocks <= c are final
+      } else {
+        __threadfence_block();
       }
       __syncwarp();
-      if (lane_on) {
-        // back to lane = pixel row: write the macroblock row out, keep its last word as carry
-        unsigned *outp = reinterpret_cast<unsigned *>(rowp + c * n);
-        if (luma) {
-          uint4 o = make_uint4(trow[0], trow[1], trow[2], trow[3]);
-          *reinterpret_cast<uint4 *>(outp) = o;
-          carry = o.w;
-        } else {
-          uint2 o = make_uint2(trow[0], trow[1]);
-          *reinterpret_cast<uint2 *>(outp) = o;
-          carry = o.y;
-        }
-      }
-      // every lane fences its own stores, then the warp agrees, then one lane publishes
-      if (last_of_band) __threadfence();
-      else __threadfence_block();
+      if (lane == 0) lprog[lr] = c + 1;
+    }
+    if (last_of_band) {
+      __threadfence();
       __syncwarp();
-      if (lane == 0) {
-        lprog[lr] = c + 1;
-        if (last_of_band) atomicExch(&gflag[band], c + 1);
-      }
+      if (lane == 0) atomicExch(&gflag[band], cols);
     }
   }
 }
