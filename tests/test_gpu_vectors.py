@@ -165,3 +165,62 @@ def test_device_resident_replay_and_checksums(engine):
     st.close()
     for f in frames:
         f.close()
+
+
+def test_4k_frames_match_oracle_checksums(engine):
+    """BASELINE config 5 frame size (3840x2160, 240x135 macroblocks, 8 DCT partitions): every frame's
+    device-side checksum equals the checksum of the oracle's picture, and the last frame is compared
+    byte for byte."""
+    import vp8_b200
+    ivf = helpers.synth_stream("--width 3840 --height 2160 --frames 4 --seed 51 --log2-parts 3 "
+                               "--pct-skip 55 --coef-density 3 --pct-empty-block 80 --altref-period 3")
+    _, payloads = vp8_b200.read_ivf(ivf)
+    ps, orc, st = vp8_b200.Parser(), helpers.Oracle(), engine.open_stream()
+    lib = engine._lib
+    try:
+        for k, p in enumerate(payloads):
+            fr = ps.parse(p)
+            want = orc.decode(fr)
+            st.decode(p)
+            assert st.dims() == (3840, 2160)
+            assert st.checksum() == lib.vp8r_checksum_i420(want, 3840, 2160), f"frame {k}"
+            if k == len(payloads) - 1:
+                assert st.read_frame() == want
+            fr.close()
+    finally:
+        st.close()
+        orc.close()
+
+
+def test_many_streams_lockstep_checksums(engine):
+    """48 independent streams of different seeds and two sizes in one lock-step batch (the bench's
+    execution pattern, band-major filter tickets included): every stream's every frame matches the
+    oracle by checksum."""
+    import vp8_b200
+    n = 48
+    ivfs = [helpers.synth_stream(f"--width {320 if k % 2 else 400} --height {240 if k % 2 else 304} --frames 5 "
+                                 f"--seed {100 + k} --log2-parts {k % 3}") for k in range(n)]
+    payloads = [vp8_b200.read_ivf(v)[1] for v in ivfs]
+    want = []
+    for k in range(n):
+        ps, orc = vp8_b200.Parser(), helpers.Oracle()
+        sums = []
+        for p in payloads[k]:
+            fr = ps.parse(p)
+            img = orc.decode(fr)
+            d = fr.desc().hdr
+            sums.append(engine._lib.vp8r_checksum_i420(img, d.width, d.height))
+            fr.close()
+        orc.close()
+        want.append(sums)
+    dec = vp8_b200.BatchDecoder(engine, n, pinned=True)
+    got = [[] for _ in range(n)]
+
+    def on_step(t, live, frames):
+        sums = engine.checksum_batch([dec.streams[i] for i in live])
+        for i, s in zip(live, sums):
+            got[i].append(s)
+
+    dec.decode(payloads, on_step=on_step)
+    dec.close()
+    assert got == want

@@ -39,6 +39,17 @@ class BatchDecoder:
         check(self._lib.vp8r_parse_batch(n, pa, da, sa, fa, self.parse_threads, None))
         return frames
 
+    def parse_into(self, frames, payloads, live):
+        """Parses payloads[i] of the live streams into caller-owned ParsedFrame objects (host threads)."""
+        n = len(live)
+        bufs = [(C.c_uint8 * len(payloads[i])).from_buffer_copy(payloads[i]) for i in live]
+        pa = (C.c_void_p * n)(*[self.parsers[i].handle for i in live])
+        da = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
+        sa = (C.c_size_t * n)(*[len(payloads[i]) for i in live])
+        fa = (C.c_void_p * n)(*[f.handle for f in frames])
+        check(self._lib.vp8r_parse_batch(n, pa, da, sa, fa, self.parse_threads, None))
+        return frames
+
     def fence(self):
         t = C.c_uint64()
         check(self._lib.vp8r_engine_fence(self.engine.handle, C.byref(t)))

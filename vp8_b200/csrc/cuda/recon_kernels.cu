@@ -176,6 +176,7 @@ __device__ __forceinline__ void Iwht4x4(int *m) {
 __device__ __forceinline__ bool WarpResidual(const DevFrameJob &job, const vp8r_mb_info &mb, int lane,
                                             short *y2_slot, int *res) {
   const unsigned mask = mb.coef_mask;
+  if (mask == 0) return false;  // warp-uniform: nothing coded in this macroblock (callers ignore res then)
   const bool has_y2 = (mb.flags & VP8R_MB_HAS_Y2) != 0;
   const int blk = lane < 24 ? lane + 1 : 0;  // index in coef_mask numbering (lane 24: Y2)
   const bool coded = lane <= 24 && ((mask >> blk) & 1);
@@ -774,14 +775,15 @@ __global__ void __launch_bounds__(256) BorderKernel(const DevFrameJob *__restric
 // ---- loop-filter wavefront -------------------------------------------------------------------
 // A frame is cut into G horizontal bands of macroblock rows; one CTA per (frame, band), one warp
 // per macroblock row.  CTAs take a ticket at start (atomic counter) and tickets map to
-// (frame, band) with the bands of a frame in increasing order, so a CTA only ever waits for a CTA
-// holding a SMALLER ticket, i.e. one that is already running or done: no co-residency assumption.
+// (band, frame) band-major, so a CTA only ever waits for a CTA holding a SMALLER ticket (the band
+// above it in the same frame), i.e. one that is already running or done: no co-residency assumption.
 // Inside a band rows synchronise through shared-memory progress counters; the last row of a band
 // also publishes to global memory for the first row of the next band (another SM, so that row's
 // "above" pixels are read with ld.cg, past the non-coherent L1).
 constexpr int kFiltWarps = 8;
 constexpr int kMaxBands = 32;
-constexpr int kBandStride = 8;  // macroblocks between cross-SM progress publications
+constexpr int kBandStride = 8;
+constexpr int kResidentCtas = 148 * 4;  // FilterKernel CTAs that fit on the chip at once (64 regs, 8 warps)  // macroblocks between cross-SM progress publications
 
 struct __align__(16) FiltTile {
   unsigned char bytes[16 * 20 + 2 * 8 * 12];  // luma rows of 16 B (+4 pad: conflict-free row
@@ -794,13 +796,20 @@ __device__ __forceinline__ int LoadFlagAcquire(const int *p) {
   return v;
 }
 
-__global__ void __launch_bounds__(kFiltWarps * 32, 4) FilterKernel(const DevFrameJob *__restrict__ jobs, int n_bands,
-                                                                   int *__restrict__ sync) {
+__global__ void __launch_bounds__(kFiltWarps * 32, 4) FilterKernel(const DevFrameJob *__restrict__ jobs, int n_frames,
+                                                                   int n_bands, int *__restrict__ sync) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_ticket;
   if (threadIdx.x == 0) s_ticket = atomicAdd(&sync[0], 1);
   __syncthreads();
-  const int frame = s_ticket / n_bands, band = s_ticket - frame * n_bands;
+  // Band-major ticket order: band b of every frame before band b+1 of any.  When the grid exceeds
+  // what is resident, the CTAs that hold SM slots are then the bands that can actually run (band
+  // b+1 becomes runnable ~1.5 macroblock steps per row after band b), not bands parked on a flag.
+  // (When everything is resident at once the order is irrelevant for progress; frame-major then
+  // keeps the bands of a frame on neighbouring SMs, which measured ~12 % faster.)
+  const bool band_major = n_frames * n_bands > kResidentCtas;
+  const int band = band_major ? s_ticket / n_frames : s_ticket % n_bands;
+  const int frame = band_major ? s_ticket - band * n_frames : s_ticket / n_bands;
   const DevFrameJob &job = jobs[frame];
   const int rows = job.mb_rows, cols = job.mb_cols;
   const int rpb = (rows + n_bands - 1) / n_bands;
@@ -1021,7 +1030,7 @@ cudaError_t LaunchFilter(const DevFrameJob *jobs, int n_frames, int max_rows, in
   if (e != cudaSuccess) return e;
   const int rpb = (max_rows + n_bands - 1) / n_bands;
   size_t smem = ((size_t(rpb) * 4 + 15) & ~size_t(15)) + sizeof(FiltTile) * kFiltWarps;
-  FilterKernel<<<n_frames * n_bands, kFiltWarps * 32, smem, st>>>(jobs, n_bands, sync);
+  FilterKernel<<<n_frames * n_bands, kFiltWarps * 32, smem, st>>>(jobs, n_frames, n_bands, sync);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   BorderKernel<<<dim3(8, n_frames), 256, 0, st>>>(jobs);
