@@ -780,10 +780,11 @@ __global__ void __launch_bounds__(256) BorderKernel(const DevFrameJob *__restric
 // Inside a band rows synchronise through shared-memory progress counters; the last row of a band
 // also publishes to global memory for the first row of the next band (another SM, so that row's
 // "above" pixels are read with ld.cg, past the non-coherent L1).
-constexpr int kFiltWarps = 8;
-constexpr int kMaxBands = 32;
+constexpr int kFiltWarps = 4;
+constexpr int kMaxBands = 64;
 constexpr int kBandStride = 8;
-constexpr int kResidentCtas = 148 * 4;  // FilterKernel CTAs that fit on the chip at once (64 regs, 8 warps)  // macroblocks between cross-SM progress publications
+constexpr int kFiltCtasPerSm = 7;  // 72 registers: measured best trade of occupancy (28 warps/SM) against spills
+constexpr int kResidentCtas = 148 * kFiltCtasPerSm;  // FilterKernel CTAs that fit on the chip at once
 
 struct __align__(16) FiltTile {
   unsigned char bytes[16 * 20 + 2 * 8 * 12];  // luma rows of 16 B (+4 pad: conflict-free row
@@ -796,7 +797,7 @@ __device__ __forceinline__ int LoadFlagAcquire(const int *p) {
   return v;
 }
 
-__global__ void __launch_bounds__(kFiltWarps * 32, 4) FilterKernel(const DevFrameJob *__restrict__ jobs, int n_frames,
+__global__ void __launch_bounds__(kFiltWarps * 32, kFiltCtasPerSm) FilterKernel(const DevFrameJob *__restrict__ jobs, int n_frames,
                                                                    int n_bands, int *__restrict__ sync) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_ticket;

@@ -488,7 +488,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
   }
   {
     ScopedTimer t(e, 2);
-    const int need_sync = 1 + n * 32;
+    const int need_sync = 1 + n * 64;
     if (need_sync > e->sync_cap) {
       CU_TRY(cudaStreamSynchronize(e->st));
       if (e->d_sync) cudaFree(e->d_sync);
