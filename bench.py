@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--streams", type=int, default=256, help="independent 1080p streams per GPU")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--serial-setup", action="store_true", help="generate the streams one at a time (for runs under ncu)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -185,7 +186,7 @@ def main():
     tmp = tempfile.mkdtemp()
     from concurrent.futures import ThreadPoolExecutor
     paths = [os.path.join(tmp, f"s{k}.ivf") for k in range(S)]
-    with ThreadPoolExecutor(max_workers=max(1, (os.cpu_count() or 1) // max(1, world))) as ex:
+    with ThreadPoolExecutor(max_workers=1 if args.serial_setup else max(1, (os.cpu_count() or 1) // max(1, world))) as ex:
         list(ex.map(lambda k: synth_stream(7122 + rank * S + k, paths[k]), range(S)))
     payloads = [vp8_b200.read_ivf(p)[1] for p in paths]
     shutil.rmtree(tmp, ignore_errors=True)

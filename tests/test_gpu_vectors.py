@@ -224,3 +224,51 @@ def test_many_streams_lockstep_checksums(engine):
     dec.decode(payloads, on_step=on_step)
     dec.close()
     assert got == want
+
+
+def test_randomised_streams_against_oracle(engine):
+    """60 small streams with randomised generator settings (all four bitstream versions, both loop
+    filters, every sharpness, 1-8 partitions, odd sizes, dense SPLIT / intra / B_PRED mixes, GOP
+    lengths) decoded as one lock-step batch; every frame of every stream must equal the oracle's
+    picture (device checksum vs host checksum of the oracle output)."""
+    import random
+    import vp8_b200
+    rng = random.Random(20261018)
+    cfgs = []
+    for k in range(60):
+        w, h = rng.choice([(16, 16), (17, 33), (48, 64), (96, 80), (130, 98), (176, 144), (250, 120), (320, 16)])
+        cfgs.append(f"--width {w} --height {h} --frames {rng.randint(3, 9)} --seed {1000 + k} "
+                    f"--version {rng.randint(0, 3)} --filter-type {rng.randint(0, 1)} --sharpness {rng.randint(0, 7)} "
+                    f"--lf {rng.choice([0, 1, 8, 24, 40, 63])} --q {rng.choice([0, 10, 40, 90, 127])} "
+                    f"--log2-parts {rng.randint(0, 3)} --key-interval {rng.choice([0, 2, 4])} "
+                    f"--segmentation {rng.randint(0, 1)} --lf-deltas {rng.randint(0, 1)} "
+                    f"--pct-intra {rng.choice([0, 8, 40, 100])} --pct-split {rng.choice([0, 10, 60])} "
+                    f"--pct-new {rng.choice([10, 30])} --pct-skip {rng.choice([0, 35, 90])} "
+                    f"--pct-bpred {rng.choice([0, 25, 100])} --coef-density {rng.randint(1, 8)} "
+                    f"--pct-empty-block {rng.choice([0, 45, 90])} --golden-period {rng.choice([0, 2, 5])} "
+                    f"--altref-period {rng.choice([0, 3, 4])} --hidden-altref {rng.randint(0, 1)}")
+    payloads = [vp8_b200.read_ivf(helpers.synth_stream(c))[1] for c in cfgs]
+    lib = engine._lib
+    want = []
+    for pl in payloads:
+        ps, orc = vp8_b200.Parser(), helpers.Oracle()
+        sums = []
+        for p in pl:
+            fr = ps.parse(p)
+            img = orc.decode(fr)
+            d = fr.desc().hdr
+            sums.append(lib.vp8r_checksum_i420(img, d.width, d.height))
+            fr.close()
+        orc.close()
+        want.append(sums)
+    dec = vp8_b200.BatchDecoder(engine, len(cfgs), pinned=True)
+    got = [[] for _ in cfgs]
+
+    def on_step(t, live, frames):
+        for i, s in zip(live, engine.checksum_batch([dec.streams[i] for i in live])):
+            got[i].append(s)
+
+    dec.decode(payloads, on_step=on_step)
+    dec.close()
+    bad = [cfgs[i] for i in range(len(cfgs)) if got[i] != want[i]]
+    assert not bad, bad[:3]

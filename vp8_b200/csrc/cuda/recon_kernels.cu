@@ -783,12 +783,15 @@ __global__ void __launch_bounds__(256) BorderKernel(const DevFrameJob *__restric
 constexpr int kFiltWarps = 4;
 constexpr int kMaxBands = 64;
 constexpr int kBandStride = 8;
-constexpr int kFiltCtasPerSm = 7;  // 72 registers: measured best trade of occupancy (28 warps/SM) against spills
+constexpr int kFiltCtasPerSm = 8;  // 72 registers: measured best trade of occupancy (28 warps/SM) against spills
 constexpr int kResidentCtas = 148 * kFiltCtasPerSm;  // FilterKernel CTAs that fit on the chip at once
 
+constexpr int kTilePitch = 20;  // bytes between tile rows, the same for luma and chroma so that
+                                // every row/column offset below is a compile-time immediate
 struct __align__(16) FiltTile {
-  unsigned char bytes[16 * 20 + 2 * 8 * 12];  // luma rows of 16 B (+4 pad: conflict-free row
-                                              // stores), then U and V rows of 8 B (+4 pad)
+  unsigned char bytes[(16 + 8 + 8) * kTilePitch];  // 16 luma rows, 8 U rows, 8 V rows (16 or 8 B
+                                                   // used per row; the pad makes row stores
+                                                   // conflict-free)
 };
 
 __device__ __forceinline__ int LoadFlagAcquire(const int *p) {
@@ -839,10 +842,9 @@ __global__ void __launch_bounds__(kFiltWarps * 32, kFiltCtasPerSm) FilterKernel(
   // Transposition tile of this warp, addressed by integer offsets from the dynamic shared-memory
   // base so that every access stays an LDS/STS (no generic addressing).
   unsigned char *const tb = reinterpret_cast<unsigned char *>(tiles + warp);
-  const int tpitch = luma ? 20 : 12;  // bytes between tile rows
-  const int tbase = luma ? 0 : 320 + (lane < 24 ? 0 : 96);
-  const int trow_off = tbase + line * tpitch;  // this lane's pixel row
-  const int tcol_off = tbase + line;           // this lane's pixel column
+  const int tbase = luma ? 0 : (lane < 24 ? 16 : 24) * kTilePitch;
+  const int trow_off = tbase + line * kTilePitch;  // this lane's pixel row
+  const int tcol_off = tbase + line;               // this lane's pixel column
 
   for (int lr = warp; lr < r1 - r0; lr += kFiltWarps) {
     const int r = r0 + lr;
@@ -950,7 +952,7 @@ __global__ void __launch_bounds__(kFiltWarps * 32, kFiltCtasPerSm) FilterKernel(
           v[0] = a4[0]; v[1] = a4[1]; v[2] = a4[2]; v[3] = a4[3];
 #pragma unroll
           for (int y = 0; y < 16; ++y)
-            if (y < n) v[4 + y] = tb[tcol_off + y * tpitch];
+            if (y < n) v[4 + y] = tb[tcol_off + y * kTilePitch];
           if (has_above) LfEdge<true>(v, lim, simple);
           if (inner) {
 #pragma unroll
@@ -963,7 +965,7 @@ __global__ void __launch_bounds__(kFiltWarps * 32, kFiltCtasPerSm) FilterKernel(
           }
 #pragma unroll
           for (int y = 0; y < 16; ++y)
-            if (y < n) tb[tcol_off + y * tpitch] = (unsigned char)v[4 + y];
+            if (y < n) tb[tcol_off + y * kTilePitch] = (unsigned char)v[4 + y];
         }
         __syncwarp();
         if (lane_on) {

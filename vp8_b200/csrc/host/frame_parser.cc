@@ -263,23 +263,18 @@ int16_t FrameParser::ReadMvComponent(const uint8_t *p) {  // bitstream_parser.cc
 // coefficient is non-zero (a block of explicit zero tokens returns 0 and leaves zeros in dst).
 // *nz_after_dequant mirrors what the reference later derives from the DEQUANTISED int16 values
 // (decode_frame.cc:6-47): a product that wraps to 0 in int16 counts as zero there.
-int FrameParser::ReadCoefBlock(BoolReader &br, int type, int ctx, int first, int dc_f, int ac_f,
-                               int16_t *dst, bool *nz_after_dequant) {
+int FrameParser::ReadCoefTokens(BoolReader &br, int type, int ctx, int first, int dc_f, int ac_f,
+                                int16_t *dst, bool *nz_after_dequant) {
   const uint8_t(*bands)[3][11] = probs_.coef[type];
   int n = first;
   const uint8_t *p = bands[kBand[n]][ctx];
   int any = 0;
   bool dq_any = false;
-  // Most blocks are empty: their first symbol is the end-of-block branch.  Decide that before
-  // touching the destination.
-  if (!br.Bit(p[0])) {
-    *nz_after_dequant = false;
-    return 0;
-  }
   std::memset(dst, 0, 32);
   bool first_symbol = true;
   while (n < 16) {
-    if (!first_symbol && !br.Bit(p[0])) break;  // end of block (not coded right after a zero token)
+    if (!first_symbol && !br.Bit(p[0])) break;  // end of block (not coded right after a zero token;
+                                                // the block's first end-of-block test is in ReadCoefBlock)
     first_symbol = false;
     while (!br.Bit(p[1])) {    // zero token(s)
       if (++n == 16) goto done;

@@ -58,8 +58,19 @@ class FrameParser {
   int ParseMacroblocks(vp8r_frame *out);
   void ParseInterMb(int r, int c, int idx, int ref, vp8r_mb_info *mb, vp8r_frame *out, bool *split);
   int16_t ReadMvComponent(const uint8_t *p);
-  int ReadCoefBlock(BoolReader &br, int type, int ctx, int first, int dc_f, int ac_f, int16_t *dst,
-                    bool *nz_after_dequant);
+  // Most blocks are empty: their first symbol is the end-of-block branch.  That test is inlined
+  // into the macroblock loop; only non-empty blocks pay for the call into the token loop.
+  inline int ReadCoefBlock(BoolReader &br, int type, int ctx, int first, int dc_f, int ac_f, int16_t *dst,
+                           bool *nz_after_dequant) {
+    static constexpr uint8_t kFirstBand[2] = {0, 1};  // band of coefficient 0 / coefficient 1
+    if (!br.Bit(probs_.coef[type][kFirstBand[first]][ctx][0])) {
+      *nz_after_dequant = false;
+      return 0;
+    }
+    return ReadCoefTokens(br, type, ctx, first, dc_f, ac_f, dst, nz_after_dequant);
+  }
+  int ReadCoefTokens(BoolReader &br, int type, int ctx, int first, int dc_f, int ac_f, int16_t *dst,
+                     bool *nz_after_dequant);
   bool EnsurePayload(vp8r_frame *out, size_t blocks_needed);
   bool BuildIntraLevels(vp8r_frame *out);
   static constexpr unsigned kMaxFlatIntraLevels = 48;
