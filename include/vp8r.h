@@ -195,6 +195,11 @@ VP8R_API int vp8r_stream_dims(const vp8r_stream *s, int *width, int *height);
 VP8R_API int vp8r_read_batch(vp8r_engine *e, int n, vp8r_stream *const *streams,
                              uint8_t *const *dst, const size_t *cap, int async);
 VP8R_API int vp8r_stream_read_frame(vp8r_stream *s, uint8_t *dst, size_t cap);
+/* Same output, but cropped and packed ON THE DEVICE (one kernel for all n frames) and moved with
+ * ONE contiguous copy: frame i lands at dst + i*stride (stride >= frame bytes).  For many streams
+ * this replaces 3*n pitched copies per time step. */
+VP8R_API int vp8r_read_batch_packed(vp8r_engine *e, int n, vp8r_stream *const *streams, uint8_t *dst,
+                                    size_t stride, int async);
 
 /* Device-side checksum of the cropped I420 image: low word sum(b_i), high word
  * sum((i+1)*b_i), both mod 2^32, i = byte index in the Y,U,V stream.  For parity checks at sizes

@@ -132,3 +132,49 @@ def test_parsed_frame_accounting(built):
         assert at == (d.hdr.intra_levels_at if d.hdr.n_intra_levels else d.hdr.n_payload_blocks) and coef == d.hdr.n_coef_blocks
         assert split == d.hdr.n_split_mbs and inter == d.hdr.n_inter_mbs
         fr.close()
+
+
+def test_parser_survives_corrupted_streams(built):
+    """Bit flips, truncations and garbage: the parser must return a status (never crash or hang), and
+    whatever it accepts must still satisfy the array invariants the kernels rely on."""
+    import vp8_b200
+    from vp8_b200._capi import Vp8rError
+    rng = random.Random(99)
+    base = helpers.synth_stream("--width 96 --height 80 --frames 6 --seed 5 --log2-parts 2 --pct-split 30 --pct-intra 20")
+    _, payloads = vp8_b200.read_ivf(base)
+    accepted = rejected = 0
+    for trial in range(300):
+        p = vp8_b200.Parser()
+        for k, pl in enumerate(payloads):
+            data = bytearray(pl)
+            mode = rng.randrange(4)
+            if mode == 0:
+                for _ in range(rng.randint(1, 8)):
+                    data[rng.randrange(len(data))] ^= 1 << rng.randrange(8)
+            elif mode == 1:
+                data = data[:rng.randrange(1, len(data))]
+            elif mode == 2:
+                start = rng.randrange(len(data))
+                for i in range(start, min(len(data), start + 32)):
+                    data[i] = rng.randrange(256)
+            try:
+                fr = p.parse(bytes(data))
+            except Vp8rError as e:
+                assert 1 <= e.code <= 7
+                rejected += 1
+                continue
+            accepted += 1
+            d = fr.desc()
+            n_mb = d.hdr.mb_cols * d.hdr.mb_rows
+            assert 0 < n_mb <= 1 << 20
+            limit = d.hdr.intra_levels_at if d.hdr.n_intra_levels else d.hdr.n_payload_blocks
+            for i in range(n_mb):
+                mb = d.mbs[i]
+                assert mb.coef_offset + bin(mb.coef_mask).count("1") <= limit
+                assert ((mb.flags >> 11) & 63) <= 63 and mb.coef_mask < (1 << 25)
+                if (mb.flags & 1) and ((mb.flags >> 3) & 7) == 4:
+                    assert mb.aux[0] + 2 <= limit
+                if not (mb.flags & 1) and ((mb.flags >> 3) & 7) == 4:
+                    assert all(((mb.aux[b >> 3] >> ((b & 7) * 4)) & 15) <= 9 for b in range(16))
+            fr.close()
+    assert accepted > 100 and rejected > 20

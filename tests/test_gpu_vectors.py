@@ -272,3 +272,27 @@ def test_randomised_streams_against_oracle(engine):
     dec.close()
     bad = [cfgs[i] for i in range(len(cfgs)) if got[i] != want[i]]
     assert not bad, bad[:3]
+
+
+def test_packed_readback_equals_pitched_readback(engine):
+    """vp8r_read_batch_packed (device-side crop + I420 pack, one copy) against vp8r_stream_read_frame
+    for even, odd and tiny frame sizes in one batch."""
+    import ctypes as C
+    import vp8_b200
+    sizes = [(176, 144), (175, 143), (33, 17), (16, 16), (130, 98), (320, 240)]
+    ivfs = [helpers.synth_stream(f"--width {w} --height {h} --frames 3 --seed {70 + k}") for k, (w, h) in enumerate(sizes)]
+    streams = [engine.open_stream() for _ in sizes]
+    try:
+        for st, ivf in zip(streams, ivfs):
+            for p in vp8_b200.read_ivf(ivf)[1]:
+                st.decode(p)
+        stride = max(st.frame_bytes() for st in streams) + 5  # deliberately unaligned stride
+        buf = (C.c_uint8 * (stride * len(streams)))()
+        engine.read_batch_packed(streams, C.addressof(buf), stride)
+        raw = bytes(buf)
+        for k, st in enumerate(streams):
+            want = st.read_frame()
+            assert raw[k * stride:k * stride + len(want)] == want, sizes[k]
+    finally:
+        for st in streams:
+            st.close()

@@ -58,10 +58,13 @@ class BatchDecoder:
     def wait(self, ticket):
         check(self._lib.vp8r_engine_wait(self.engine.handle, ticket))
 
-    def decode(self, payloads, out_ring=None, on_step=None):
+    def decode(self, payloads, out_ring=None, on_step=None, out_packed=None):
         """payloads[s] = list of compressed frames of stream s.  out_ring: optional list of two lists
         of (ptr, capacity) pinned host buffers, one per stream, that receive the frames of a time step
-        (ring of two steps).  on_step(t, live, frames) is called after step t has been submitted.
+        (ring of two steps).  out_packed: optional ((ptr0, ptr1), stride): two pinned host buffers; the
+        frames of a time step are cropped and packed on the device and arrive with one copy, frame k
+        of the step's live streams at ptr + k*stride.  on_step(t, live, frames) is called after step t
+        has been submitted.
         Returns (frames decoded, frames shown, h2d bytes, d2h bytes)."""
         steps = max(len(p) for p in payloads)
         decoded = shown = h2d = d2h = 0
@@ -80,6 +83,10 @@ class BatchDecoder:
                 ring = out_ring[t & 1]
                 self.engine.read_batch(streams, [ring[i][0] for i in live], [ring[i][1] for i in live], async_=True)
                 d2h += sum(s.frame_bytes() for s in streams)
+            if out_packed is not None:
+                (ptrs, stride) = out_packed
+                self.engine.read_batch_packed(streams, ptrs[t & 1], stride, async_=True)
+                d2h += len(streams) * stride
             tickets[t] = self.fence()
             if on_step:
                 on_step(t, live, frames)

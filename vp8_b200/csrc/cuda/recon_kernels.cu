@@ -1080,6 +1080,61 @@ __global__ void ChecksumKernel(const DevFrameJob *__restrict__ jobs) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// crop + pack: YUV<WRITE>::WriteFrame (src/yuv.cc:6-28) on the device.  Each job's cropped Y, U, V
+// planes are written back to back at job.pack_dst, so one contiguous copy moves any number of frames.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) PackKernel(const DevFrameJob *__restrict__ jobs) {
+  const DevFrameJob &job = jobs[blockIdx.y];
+  uint8_t *dst = job.pack_dst;
+  if (!dst) return;
+  const int w = job.width, h = job.height, cw = (w + 1) / 2, ch = (h + 1) / 2;
+  const uint8_t *py = job.cur.y, *pu = job.cur.u, *pv = job.cur.v;
+  const int pitch_y = job.pitch_y, pitch_c = job.pitch_c;
+  // 4 pixels per thread-item where the row allows it (source rows are 16-byte aligned; the
+  // destination is byte-packed, so it is written bytewise unless w % 4 == 0).
+  const int wy4 = (w + 3) / 4, wc4 = (cw + 3) / 4;
+  const int items_y = wy4 * h, items_c = wc4 * ch;
+  const int total = items_y + 2 * items_c;
+  const bool y_vec = (w & 3) == 0, c_vec = (cw & 3) == 0 && ((size_t)w * h & 3) == 0 && ((size_t)cw * ch & 3) == 0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const uint8_t *src;
+    uint8_t *d;
+    int x, n;
+    bool vec;
+    if (t < items_y) {
+      const int row = t / wy4;
+      x = (t - row * wy4) * 4;
+      src = py + (size_t)row * pitch_y + x;
+      d = dst + (size_t)row * w + x;
+      n = min(4, w - x);
+      vec = y_vec;
+    } else {
+      int u = t - items_y;
+      const int plane = u >= items_c;
+      if (plane) u -= items_c;
+      const int row = u / wc4;
+      x = (u - row * wc4) * 4;
+      src = (plane ? pv : pu) + (size_t)row * pitch_c + x;
+      d = dst + (size_t)w * h + (size_t)plane * cw * ch + (size_t)row * cw + x;
+      n = min(4, cw - x);
+      vec = c_vec;
+    }
+    const unsigned v = *reinterpret_cast<const unsigned *>(src);
+    if (vec && (((size_t)d & 3) == 0)) {
+      *reinterpret_cast<unsigned *>(d) = v;
+    } else {
+      for (int k = 0; k < n; ++k) d[k] = (uint8_t)(v >> (8 * k));
+    }
+  }
+}
+
+cudaError_t LaunchPack(const DevFrameJob *jobs, int n_frames, cudaStream_t st) {
+  dim3 grid(48, n_frames);
+  PackKernel<<<grid, 256, 0, st>>>(jobs);
+  return cudaGetLastError();
+}
+
 cudaError_t LaunchChecksum(const DevFrameJob *jobs, int n_frames, cudaStream_t st) {
   dim3 grid(64, n_frames);
   ChecksumKernel<<<grid, 256, 0, st>>>(jobs);

@@ -35,6 +35,7 @@ struct DevFrameJob {
   // output side (crop / checksum)
   int width, height;
   unsigned long long *checksum;  // optional: receives the I420 checksum
+  uint8_t *pack_dst;             // optional: receives the cropped I420 image (device memory)
 };
 
 // Uploads the constant tables (filter taps, B_PRED gather LUT).  Once per device.
@@ -50,6 +51,8 @@ cudaError_t LaunchIntraFlat(const DevFrameJob *jobs, int n_frames, int level, in
 // `sync`: device scratch of `sync_ints` ints (ticket + one progress word per (frame, band)).
 cudaError_t LaunchFilter(const DevFrameJob *jobs, int n_frames, int max_rows, int *sync, int sync_ints,
                          cudaStream_t st);
+// Device-side crop + I420 pack of each job's current surface into job.pack_dst.
+cudaError_t LaunchPack(const DevFrameJob *jobs, int n_frames, cudaStream_t st);
 // Device-side checksum of the cropped I420 image of each job's current surface.
 cudaError_t LaunchChecksum(const DevFrameJob *jobs, int n_frames, cudaStream_t st);
 

@@ -97,10 +97,14 @@ struct vp8r_engine {
   // ticket + per-(frame, band) progress words of the wavefront kernels
   int *d_sync = nullptr;
   int sync_cap = 0;
+  // device staging of packed I420 frames (vp8r_read_batch_packed)
+  uint8_t *d_pack = nullptr;
+  size_t pack_cap = 0;
   // checksum scratch
   DevFrameJob *h_cjobs = nullptr, *d_cjobs = nullptr;
   unsigned long long *d_sums = nullptr, *h_sums = nullptr;
   int cap_cjobs = 0;
+  int pack_flip = 0;
   // host-visible fences (vp8r_engine_fence / vp8r_engine_wait)
   cudaEvent_t fence_ev[16] = {};
   uint64_t fence_head = 0;
@@ -316,6 +320,7 @@ VP8R_API void vp8r_engine_destroy(vp8r_engine *e) {
   if (e->h_sums) cudaFreeHost(e->h_sums);
   if (e->d_sums) cudaFree(e->d_sums);
   if (e->d_sync) cudaFree(e->d_sync);
+  if (e->d_pack) cudaFree(e->d_pack);
   for (auto &ev : e->fence_ev)
     if (ev) cudaEventDestroy(ev);
   DrainTimers(e);
@@ -567,6 +572,68 @@ VP8R_API int vp8r_read_batch(vp8r_engine *e, int n, vp8r_stream *const *streams,
   return VP8R_OK;
 }
 
+VP8R_API int vp8r_read_batch_packed(vp8r_engine *e, int n, vp8r_stream *const *streams, uint8_t *dst, size_t stride,
+                                    int async) {
+  if (!e || n <= 0 || !streams || !dst) return VP8R_ERR_INVALID_ARG;
+  int rc = EnsureDevice(e);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    const vp8r_stream *s = streams[i];
+    if (!s || s->eng != e || !s->have_frame) {
+      SetError("stream has no reconstructed frame");
+      return VP8R_ERR_STATE;
+    }
+    if (vp8r_stream_frame_bytes(s) > stride) {
+      SetError("stride smaller than a frame");
+      return VP8R_ERR_INVALID_ARG;
+    }
+  }
+  const size_t bytes = size_t(n) * stride;
+  if (bytes > e->pack_cap) {
+    CU_TRY(cudaStreamSynchronize(e->st));
+    if (e->d_pack) cudaFree(e->d_pack);
+    e->d_pack = nullptr;
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_pack), bytes + 256));
+    e->pack_cap = bytes;
+  }
+  // job table: reuse the checksum scratch, growing it if needed
+  if (n > e->cap_cjobs) {
+    CU_TRY(cudaStreamSynchronize(e->st));
+    if (e->h_cjobs) cudaFreeHost(e->h_cjobs);
+    if (e->d_cjobs) cudaFree(e->d_cjobs);
+    if (e->h_sums) cudaFreeHost(e->h_sums);
+    if (e->d_sums) cudaFree(e->d_sums);
+    e->h_cjobs = e->d_cjobs = nullptr;
+    e->h_sums = e->d_sums = nullptr;
+    int cap = std::max(n, 64);
+    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_cjobs), sizeof(DevFrameJob) * cap * 2, cudaHostAllocDefault));
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_cjobs), sizeof(DevFrameJob) * cap * 2));
+    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_sums), sizeof(uint64_t) * cap, cudaHostAllocDefault));
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_sums), sizeof(uint64_t) * cap));
+    e->cap_cjobs = cap;
+  }
+  // Two halves of the table alternate so that an in-flight asynchronous copy of the previous call
+  // is not overwritten on the host side.
+  e->pack_flip ^= 1;
+  DevFrameJob *hj = e->h_cjobs + size_t(e->pack_flip) * e->cap_cjobs;
+  DevFrameJob *dj = e->d_cjobs + size_t(e->pack_flip) * e->cap_cjobs;
+  for (int i = 0; i < n; ++i) {
+    DevFrameJob &j = hj[i];
+    std::memset(&j, 0, sizeof(j));
+    FillJobSurfaces(streams[i], streams[i]->ref[0], &j);
+    j.pack_dst = e->d_pack + size_t(i) * stride;
+  }
+  {
+    ScopedTimer t(e, 4);
+    CU_TRY(cudaMemcpyAsync(dj, hj, sizeof(DevFrameJob) * n, cudaMemcpyHostToDevice, e->st));
+    CU_TRY(vp8r::LaunchPack(dj, n, e->st));
+    e->acc.launches_other++;
+    CU_TRY(cudaMemcpyAsync(dst, e->d_pack, bytes, cudaMemcpyDeviceToHost, e->st));
+  }
+  if (!async) CU_TRY(cudaStreamSynchronize(e->st));
+  return VP8R_OK;
+}
+
 VP8R_API int vp8r_stream_read_frame(vp8r_stream *s, uint8_t *dst, size_t cap) {
   if (!s) return VP8R_ERR_INVALID_ARG;
   vp8r_stream *ss[1] = {s};
@@ -588,8 +655,8 @@ VP8R_API int vp8r_checksum_batch(vp8r_engine *e, int n, vp8r_stream *const *stre
     e->h_cjobs = e->d_cjobs = nullptr;
     e->h_sums = e->d_sums = nullptr;
     int cap = std::max(n, 64);
-    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_cjobs), sizeof(DevFrameJob) * cap, cudaHostAllocDefault));
-    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_cjobs), sizeof(DevFrameJob) * cap));
+    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_cjobs), sizeof(DevFrameJob) * cap * 2, cudaHostAllocDefault));
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_cjobs), sizeof(DevFrameJob) * cap * 2));
     CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_sums), sizeof(uint64_t) * cap, cudaHostAllocDefault));
     CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_sums), sizeof(uint64_t) * cap));
     e->cap_cjobs = cap;

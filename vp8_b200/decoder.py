@@ -98,6 +98,13 @@ class Engine:
         ca = (C.c_size_t * n)(*caps)
         check(self._lib.vp8r_read_batch(self.handle, n, sa, pa, ca, 1 if async_ else 0))
 
+    def read_batch_packed(self, streams, dst_ptr, stride, async_=False):
+        """Device-side crop + pack of every stream's latest frame, one contiguous D2H copy:
+        frame i at dst_ptr + i*stride."""
+        n = len(streams)
+        sa = (C.c_void_p * n)(*[s.handle for s in streams])
+        check(self._lib.vp8r_read_batch_packed(self.handle, n, sa, C.c_void_p(dst_ptr), stride, 1 if async_ else 0))
+
     def sync(self):
         check(self._lib.vp8r_engine_sync(self.handle))
 
