@@ -261,7 +261,7 @@ def main():
     for f in (f for fr in resident for f in fr):
         f.close()
     dec.close()
-    e2e_dec = vp8_b200.BatchDecoder(eng, S, pinned=True)
+    e2e_dec = vp8_b200.BatchDecoder(eng, S, parse_threads=max(1, min(S, (os.cpu_count() or 1) // max(1, world))), pinned=True)
     ring_t = [torch.empty((S, FRAME_BYTES), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
     packed = ((ring_t[0].data_ptr(), ring_t[1].data_ptr()), FRAME_BYTES)  # device-side crop+pack, one D2H per step
     e2e_dec.decode(payloads, out_packed=packed)  # warm-up (allocations, pinned buffers growth)
