@@ -159,6 +159,8 @@ def main():
     ap.add_argument("--streams", type=int, default=256, help="independent 1080p streams per GPU")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-tokens", action="store_true",
+                    help="end-to-end pass: decode the DCT token partitions on the host too (default: device token kernel)")
     ap.add_argument("--serial-setup", action="store_true", help="generate the streams one at a time (for runs under ncu)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -261,7 +263,8 @@ def main():
     for f in (f for fr in resident for f in fr):
         f.close()
     dec.close()
-    e2e_dec = vp8_b200.BatchDecoder(eng, S, parse_threads=max(1, min(S, (os.cpu_count() or 1) // max(1, world))), pinned=True)
+    e2e_dec = vp8_b200.BatchDecoder(eng, S, parse_threads=max(1, min(S, (os.cpu_count() or 1) // max(1, world))), pinned=True,
+                                   tokens_on_device=not args.host_tokens)
     ring_t = [torch.empty((S, FRAME_BYTES), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
     packed = ((ring_t[0].data_ptr(), ring_t[1].data_ptr()), FRAME_BYTES)  # device-side crop+pack, one D2H per step
     e2e_dec.decode(payloads, out_packed=packed)  # warm-up (allocations, pinned buffers growth)
@@ -310,7 +313,9 @@ def main():
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "mp_per_s": e2e_value * W * H / 1e6, "steps": args.e2e_steps,
-                    "kernel_ms_per_step": (tm2.ms_inter + tm2.ms_intra + tm2.ms_filter) / max(1, args.e2e_steps + 1)},
+                    "kernel_ms_per_step": (tm2.ms_inter + tm2.ms_intra + tm2.ms_filter) / max(1, args.e2e_steps + 1),
+                    "token_kernel_ms_per_step": tm2.ms_tokens / max(1, args.e2e_steps + 1),
+                    "tokens": "host" if args.host_tokens else "device"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

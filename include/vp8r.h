@@ -79,6 +79,8 @@ typedef struct vp8r_mb_info {
 #define VP8R_MB_QSEG_SHIFT    9  /* 2 bits: row of vp8r_frame_hdr.dq used by this MB */
 #define VP8R_MB_LF_SHIFT      11 /* 6 bits: loop-filter level of this MB (0 = not filtered) */
 #define VP8R_MB_LF_INNER      0x00020000u /* filter the inner (sub-block) edges too */
+#define VP8R_MB_SKIP_COEF     0x00040000u /* mb_skip_coeff: the MB has no tokens in its DCT partition
+                                             (only meaningful in frames with deferred tokens) */
 
 /* Dequantisation factor columns of vp8r_frame_hdr.dq (src/quantizer.cc:15-53). */
 enum { VP8R_DQ_Y1_DC = 0, VP8R_DQ_Y1_AC, VP8R_DQ_Y2_DC, VP8R_DQ_Y2_AC, VP8R_DQ_UV_DC, VP8R_DQ_UV_AC };
@@ -95,7 +97,8 @@ typedef struct vp8r_frame_hdr {
   uint8_t refresh_last, refresh_golden, refresh_altref; /* key frames: all 1 */
   uint8_t copy_to_golden, copy_to_altref;               /* 0 none, 1 last, 2 other (loop.h:19-46) */
   uint8_t sign_bias_golden, sign_bias_altref;
-  uint8_t reserved0[3];
+  uint8_t reserved0[2];
+  uint8_t tokens_deferred;    /* 1: see tokens_at below */
   int16_t dq[4][6];           /* dequant factors per segment (row 0 only when segmentation is off) */
   uint32_t n_coef_blocks;     /* coefficient blocks stored in payload[] */
   uint32_t n_payload_blocks;  /* all 32-byte payload blocks (coefficients + SPLIT motion vectors) */
@@ -108,7 +111,23 @@ typedef struct vp8r_frame_hdr {
    * `intra_levels_at`: n_intra_levels+1 uint32 offsets, then the MB indices sorted by level. */
   uint32_t n_intra_levels;
   uint32_t intra_levels_at;
+  /* Deferred tokens (vp8r_parser_set_defer_tokens): the host parsed the first partition only.
+   * coef_mask / coef_offset of every MB are 0, VP8R_MB_LF_INNER only covers B_PRED / SPLIT, and the
+   * payload carries, at block `tokens_at`, a vp8r_token_hdr followed by the raw bytes of the
+   * DCT partitions; the engine's token kernel (one thread per partition, rows pipelined through
+   * the above-context as in src/bitstream_parser.cc:466-537) fills the rest on the device. */
+  uint32_t tokens_at;
 } vp8r_frame_hdr;
+
+/* Header of the deferred-token section of the payload (32-byte aligned, 1152 bytes). */
+typedef struct vp8r_token_hdr {
+  uint32_t n_parts;        /* 1, 2, 4 or 8 DCT partitions; MB row r uses partition r % n_parts */
+  uint32_t part_off[8];    /* byte offset of each partition inside the raw section */
+  uint32_t part_size[8];   /* bytes */
+  uint32_t raw_bytes;      /* size of the raw section (follows this header, zero padded by >= 16 B) */
+  uint32_t reserved[6];
+  uint8_t coef_probs[4][8][3][11]; /* token probabilities in force for this frame */
+} vp8r_token_hdr;
 
 typedef struct vp8r_frame_desc {
   vp8r_frame_hdr hdr;
@@ -137,6 +156,12 @@ VP8R_API void vp8r_parser_reset(vp8r_parser *p);
 VP8R_API vp8r_frame *vp8r_frame_create(int pinned);
 VP8R_API void vp8r_frame_destroy(vp8r_frame *f);
 VP8R_API int vp8r_frame_get_desc(const vp8r_frame *f, vp8r_frame_desc *out);
+
+/* on != 0: later vp8r_parser_parse calls read the first partition only (headers, modes, motion
+ * vectors) and attach the DCT partitions for the engine's device-side token decoder; see
+ * vp8r_frame_hdr.tokens_at.  Over-reads of a DCT partition are then reported by
+ * vp8r_engine_sync() instead of the parse call. */
+VP8R_API void vp8r_parser_set_defer_tokens(vp8r_parser *p, int on);
 
 /* Parses one compressed frame (the payload of one IVF frame record) into `out`. */
 VP8R_API int vp8r_parser_parse(vp8r_parser *p, const uint8_t *data, size_t size, vp8r_frame *out);
@@ -220,6 +245,7 @@ typedef struct vp8r_timers {
   double ms_intra;    /* dequant+IWHT+IDCT + intra prediction wavefront */
   double ms_filter;   /* loop-filter wavefront + border extension */
   double ms_h2d, ms_d2h;
+  double ms_tokens;   /* device-side token decode (frames with deferred tokens) */
   uint64_t launches_inter, launches_intra, launches_filter, launches_other;
   uint64_t frames, coef_blocks;
   uint64_t alg_bytes; /* sum over frames of 1.5*Wa*Ha*(1+is_inter) + 32*n_coef_blocks */

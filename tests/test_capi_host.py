@@ -24,7 +24,8 @@ def test_header_and_library_agree(built):
 def test_struct_layout(built):
     from vp8_b200 import _capi
     assert C.sizeof(_capi.MbInfo) == 32
-    assert C.sizeof(_capi.FrameHdr) == 8 + 16 + 48 + 24
+    assert C.sizeof(_capi.FrameHdr) == 8 + 16 + 48 + 28
+    assert C.sizeof(_capi.TokenHdr) == 1152
 
 
 def test_engine_fails_loudly_without_gpu(built):
@@ -178,3 +179,58 @@ def test_parser_survives_corrupted_streams(built):
                     assert all(((mb.aux[b >> 3] >> ((b & 7) * 4)) & 15) <= 9 for b in range(16))
             fr.close()
     assert accepted > 100 and rejected > 20
+
+
+def test_deferred_token_parse_matches_full_parse(built):
+    """vp8r_parser_set_defer_tokens: the first-partition half of the parse is unchanged (modes, motion
+    vectors, loop-filter levels, intra levels), coefficient fields are left for the device, and the DCT
+    partitions + the frame's token probabilities are attached to the payload."""
+    import ctypes as C
+    import vp8_b200
+    from vp8_b200._capi import TokenHdr
+    INNER, SKIP = 0x20000, 0x40000
+    streams = [open(v, "rb").read() for v in helpers.vectors()[:6]]
+    streams.append(helpers.synth_stream("--width 176 --height 144 --frames 6 --seed 3 --log2-parts 3 --pct-split 30 --pct-intra 20"))
+    for data in streams:
+        _, payloads = vp8_b200.read_ivf(data)
+        full, lazy = vp8_b200.Parser(), vp8_b200.Parser()
+        lazy.set_defer_tokens(True)
+        for pl in payloads:
+            a, b = full.parse(pl), lazy.parse(pl)
+            da, db = a.desc(), b.desc()
+            assert db.hdr.tokens_deferred == 1 and da.hdr.tokens_deferred == 0
+            for f in ("width", "height", "mb_cols", "mb_rows", "key_frame", "version", "show_frame", "filter_type",
+                      "loop_filter_level", "sharpness_level", "refresh_last", "refresh_golden", "refresh_altref",
+                      "copy_to_golden", "copy_to_altref", "n_inter_mbs", "n_split_mbs", "n_intra_levels"):
+                assert getattr(da.hdr, f) == getattr(db.hdr, f), f
+            assert bytes(da.hdr.dq) == bytes(db.hdr.dq)
+            n_mb = da.hdr.mb_cols * da.hdr.mb_rows
+            for i in range(n_mb):
+                ma, mb = da.mbs[i], db.mbs[i]
+                assert (ma.flags & ~INNER) == (mb.flags & ~(INNER | SKIP))
+                assert mb.coef_mask == 0 and mb.coef_offset == 0
+                if mb.flags & SKIP:
+                    assert ma.coef_mask == 0
+                bpred_or_split = ((ma.flags >> 3) & 7) == 4
+                assert bool(mb.flags & INNER) == bpred_or_split
+                assert bool(ma.flags & INNER) == (bpred_or_split or ma.coef_mask != 0)
+                assert tuple(ma.mv) == tuple(mb.mv)
+                if (ma.flags & 1) and bpred_or_split:  # SPLIT: same 16 motion vectors
+                    assert da.payload[ma.aux[0] * 16: ma.aux[0] * 16 + 32] == db.payload[mb.aux[0] * 16: mb.aux[0] * 16 + 32]
+                else:
+                    assert tuple(ma.aux) == tuple(mb.aux)
+            th = C.cast(C.addressof(db.payload.contents) + db.hdr.tokens_at * 32, C.POINTER(TokenHdr)).contents
+            assert th.n_parts in (1, 2, 4, 8)
+            tag = pl[0] | pl[1] << 8 | pl[2] << 16
+            first = (10 if not (tag & 1) else 3) + (tag >> 5)
+            total = len(pl) - first - 3 * (th.n_parts - 1)
+            got = sum(th.part_size[k] for k in range(th.n_parts))
+            # a last partition shorter than 2 bytes is treated as absent, like the host reader does
+            assert got == total or (th.part_size[th.n_parts - 1] == 0 and total - got < 2)
+            raw = C.string_at(C.addressof(th) + C.sizeof(TokenHdr), th.raw_bytes)
+            at = first + 3 * (th.n_parts - 1)
+            for k in range(th.n_parts):
+                assert raw[th.part_off[k]: th.part_off[k] + th.part_size[k]] == pl[at: at + th.part_size[k]]
+                at += th.part_size[k]
+            a.close()
+            b.close()

@@ -296,3 +296,96 @@ def test_packed_readback_equals_pitched_readback(engine):
     finally:
         for st in streams:
             st.close()
+
+
+# ---- device-side token decode (deferred tokens) ----------------------------------
+def _decode_deferred(engine, payloads):
+    """All frames of one stream with the DCT partitions decoded on the device; returns the I420 of
+    every frame (shown or not) and the show flags."""
+    import vp8_b200
+    ps = vp8_b200.Parser()
+    ps.set_defer_tokens(True)
+    st = engine.open_stream()
+    out, shown = [], []
+    try:
+        for p in payloads:
+            fr = ps.parse(p, pinned=True)
+            assert fr.desc().hdr.tokens_deferred == 1
+            engine.reconstruct_batch([st], [fr])
+            engine.sync()
+            out.append(st.read_frame())
+            shown.append(bool(fr.desc().hdr.show_frame))
+            fr.close()
+    finally:
+        st.close()
+        ps.close()
+    return out, shown
+
+
+@pytest.mark.parametrize("ivf", helpers.vectors(), ids=lambda p: os.path.basename(p)[:-4])
+def test_device_tokens_match_golden_and_oracle(engine, ivf):
+    """Host parses the first partition only; K_tokens decodes the DCT partitions.  Every frame byte
+    for byte against host parser -> oracle, shown frames against the golden MD5s."""
+    import vp8_b200
+    gold = helpers.golden_md5(ivf)
+    _, payloads = vp8_b200.read_ivf(ivf)
+    got, shown = _decode_deferred(engine, payloads)
+    ps, orc = vp8_b200.Parser(), helpers.Oracle()
+    k_shown = 0
+    for k, p in enumerate(payloads):
+        fr = ps.parse(p)
+        want = orc.decode(fr)
+        fr.close()
+        d = first_diff(got[k], want)
+        assert d < 0, f"frame {k}: first differing byte {d} (of {len(want)})"
+        if shown[k]:
+            assert helpers.md5(got[k]) == gold[k_shown][0]
+            k_shown += 1
+    assert k_shown == len(gold)
+    orc.close()
+
+
+@pytest.mark.parametrize("name", sorted(helpers.synth_manifest().keys()))
+def test_device_tokens_synthetic_streams(engine, name):
+    """Same, on the synthetic streams (1/2/4/8 DCT partitions, segment quantisers, 1080p)."""
+    import vp8_b200
+    m = helpers.synth_manifest()[name]
+    _, payloads = vp8_b200.read_ivf(helpers.synth_stream(m["args"]))
+    got, shown = _decode_deferred(engine, payloads)
+    gold = helpers.synth_golden(name)
+    imgs = [g for g, s in zip(got, shown) if s]
+    assert len(imgs) == len(gold)
+    for k, (img, md5) in enumerate(zip(imgs, gold)):
+        assert helpers.md5(img) == md5, f"{name} shown frame {k}"
+
+
+def test_device_tokens_batched_and_truncated(engine):
+    """Batched lock-step decode with device tokens == host tokens (device checksums), and an
+    over-read DCT partition is reported by vp8r_engine_sync as VP8R_ERR_TRUNCATED."""
+    import vp8_b200
+    from vp8_b200._capi import Vp8rError
+    ivfs = [helpers.synth_stream(f"--width 320 --height 192 --frames 5 --seed {70 + k} --log2-parts {k % 4}") for k in range(6)]
+    payloads = [vp8_b200.read_ivf(d)[1] for d in ivfs]
+    sums = []
+    for dev in (False, True):
+        dec = vp8_b200.BatchDecoder(engine, len(ivfs), pinned=True, tokens_on_device=dev)
+        per_step = []
+        dec.decode(payloads, on_step=lambda t, live, frames: per_step.append(engine.checksum_batch([dec.streams[i] for i in live])))
+        sums.append(per_step)
+        dec.close()
+    assert sums[0] == sums[1]
+    # cut the tail of the last partition of a frame with many tokens: the token kernel must flag it
+    ps = vp8_b200.Parser()
+    ps.set_defer_tokens(True)
+    st = engine.open_stream()
+    key = payloads[0][0]
+    first_size = (key[0] | key[1] << 8 | key[2] << 16) >> 5
+    keep = 10 + first_size + (len(key) - 10 - first_size) // 3
+    fr = ps.parse(key[:keep], pinned=True)
+    engine.reconstruct_batch([st], [fr])
+    with pytest.raises(Vp8rError) as ei:
+        engine.sync()
+    assert ei.value.code == 4
+    engine.sync()  # the flag is cleared once reported
+    fr.close()
+    st.close()

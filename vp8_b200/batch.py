@@ -14,12 +14,16 @@ from .decoder import ParsedFrame, Parser
 
 
 class BatchDecoder:
-    def __init__(self, engine, n_streams, parse_threads=None, pinned=True):
+    def __init__(self, engine, n_streams, parse_threads=None, pinned=True, tokens_on_device=False):
         self.engine = engine
         self._lib = engine._lib
         self.n = n_streams
         self.parse_threads = parse_threads or min(n_streams, os.cpu_count() or 1)
         self.parsers = [Parser() for _ in range(n_streams)]
+        self.tokens_on_device = tokens_on_device
+        if tokens_on_device:  # host: headers, modes, motion vectors; device: DCT token partitions
+            for p in self.parsers:
+                p.set_defer_tokens(True)
         self.streams = [engine.open_stream() for _ in range(n_streams)]
         self.slots = [[ParsedFrame(pinned=pinned) for _ in range(n_streams)] for _ in range(2)]
 

@@ -36,11 +36,20 @@ struct DevFrameJob {
   int width, height;
   unsigned long long *checksum;  // optional: receives the I420 checksum
   uint8_t *pack_dst;             // optional: receives the cropped I420 image (device memory)
+  // deferred tokens (K_tokens): vp8r_token_hdr + raw DCT partitions inside the frame's payload,
+  // and the frame's device coefficient area (first block index relative to `payload`)
+  const uint8_t *tok_hdr;
+  uint32_t coef_base;
+  int *status;                   // device-visible error word (bit 0: a DCT partition was over-read)
 };
 
 // Uploads the constant tables (filter taps, B_PRED gather LUT).  Once per device.
 cudaError_t InitKernelTables();
 
+// K_tokens: device-side token decode of every job with tok_hdr != nullptr (see token_kernel.cu).
+cudaError_t LaunchTokens(const DevFrameJob *jobs, int n_frames, int max_cols, cudaStream_t st);
+// Blocks (32 B) of device coefficient area a frame with deferred tokens needs.
+inline size_t TokenCoefBlocks(int mb_cols, int mb_rows) { return size_t(mb_cols) * mb_rows * 25; }
 // K_inter: dequant + IWHT/IDCT + motion compensation + residual add for every inter MB.
 cudaError_t LaunchInter(const DevFrameJob *jobs, int n_frames, int max_mbs, cudaStream_t st);
 // K_intra: dequant + IWHT/IDCT + intra prediction as a per-frame macroblock wavefront.

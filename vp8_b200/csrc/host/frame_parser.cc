@@ -201,15 +201,25 @@ int FrameParser::ParseHeader(const uint8_t *data, size_t size, vp8r_frame *out) 
   size_t sizes_at = tag_size + first_size;
   size_t off = sizes_at + 3 * size_t(n_dct_parts_ - 1);
   if (off >= size && n_dct_parts_ > 1) return Fail(VP8R_ERR_TRUNCATED, "partition size table exceeds the frame");
-  for (int i = 0; i < 8; ++i) dct_[i].Init(nullptr, 0);
+  for (int i = 0; i < 8; ++i) {
+    dct_[i].Init(nullptr, 0);
+    dct_data_[i] = nullptr;
+    dct_size_[i] = 0;
+  }
   for (int i = 0; i + 1 < n_dct_parts_; ++i) {
     const uint8_t *s = data + sizes_at + 3 * i;
     size_t count = size_t(s[0]) | (size_t(s[1]) << 8) | (size_t(s[2]) << 16);
     if (off + count >= size) return Fail(VP8R_ERR_TRUNCATED, "DCT partition exceeds the frame");
     dct_[i].Init(data + off, count);
+    dct_data_[i] = data + off;
+    dct_size_[i] = count;
     off += count;
   }
-  if (off < size && size - off >= 2) dct_[n_dct_parts_ - 1].Init(data + off, size - off);
+  if (off < size && size - off >= 2) {
+    dct_[n_dct_parts_ - 1].Init(data + off, size - off);
+    dct_data_[n_dct_parts_ - 1] = data + off;
+    dct_size_[n_dct_parts_ - 1] = size - off;
+  }
 
   // Quantiser indices (bitstream_parser.cc:229-273).
   y_ac_qi_ = int(br.Literal(7));
@@ -523,7 +533,11 @@ int FrameParser::ParseMacroblocks(vp8r_frame *out) {
       const int16_t *dq = h.dq[qseg];
       uint32_t mask = 0;
       mb->coef_offset = h.n_payload_blocks;
-      if (!skip) {
+      if (defer_tokens_) {
+        // The device token decoder fills coef_mask / coef_offset and completes VP8R_MB_LF_INNER.
+        mb->coef_offset = 0;
+        if (skip) mb->flags |= VP8R_MB_SKIP_COEF;
+      } else if (!skip) {
         tok.MarkUsed();
         int16_t *dst = out->payload() + size_t(h.n_payload_blocks) * 16;
         uint32_t stored = 0;
@@ -670,6 +684,39 @@ bool FrameParser::BuildIntraLevels(vp8r_frame *out) {
   return true;
 }
 
+// Deferred tokens: token header (partition table + the probabilities in force) and the raw bytes of
+// the DCT partitions, appended to the payload so that the frame still travels as one blob.
+bool FrameParser::AttachTokenPartitions(vp8r_frame *out) {
+  vp8r_frame_hdr &h = out->hdr;
+  static_assert(sizeof(vp8r_token_hdr) == 1152, "vp8r_token_hdr layout");
+  size_t raw = 0;
+  for (int i = 0; i < n_dct_parts_; ++i) raw += (dct_size_[i] + 3) & ~size_t(3);
+  const size_t raw_padded = (raw + 16 + 31) & ~size_t(31);
+  const size_t blocks = (sizeof(vp8r_token_hdr) + raw_padded) / 32;
+  if (!EnsurePayload(out, size_t(h.n_payload_blocks) + blocks)) return false;
+  uint8_t *base = reinterpret_cast<uint8_t *>(out->payload() + size_t(h.n_payload_blocks) * 16);
+  vp8r_token_hdr *th = reinterpret_cast<vp8r_token_hdr *>(base);
+  std::memset(th, 0, 96);
+  th->n_parts = uint32_t(n_dct_parts_);
+  uint8_t *dst = base + sizeof(vp8r_token_hdr);
+  size_t at = 0;
+  for (int i = 0; i < n_dct_parts_; ++i) {
+    th->part_off[i] = uint32_t(at);
+    th->part_size[i] = uint32_t(dct_size_[i]);
+    if (dct_size_[i]) std::memcpy(dst + at, dct_data_[i], dct_size_[i]);
+    size_t end = at + dct_size_[i];
+    at = (end + 3) & ~size_t(3);
+    std::memset(dst + end, 0, at - end);
+  }
+  std::memset(dst + at, 0, raw_padded - at);
+  th->raw_bytes = uint32_t(raw_padded);
+  std::memcpy(th->coef_probs, probs_.coef, sizeof(th->coef_probs));
+  h.tokens_deferred = 1;
+  h.tokens_at = h.n_payload_blocks;
+  h.n_payload_blocks += uint32_t(blocks);
+  return true;
+}
+
 int FrameParser::Parse(const uint8_t *data, size_t size, vp8r_frame *out) {
   if (!data || !out) return Fail(VP8R_ERR_INVALID_ARG, "null argument");
   out->DropDeviceCopy();
@@ -712,9 +759,12 @@ int FrameParser::Parse(const uint8_t *data, size_t size, vp8r_frame *out) {
   if (!out->Reserve(out->mb_bytes() + 64 * 1024, 0)) return Fail(VP8R_ERR_NOMEM, "out of host memory");
 
   rc = ParseMacroblocks(out);
+  bool ok = rc == VP8R_OK;
+  if (ok && !key_frame_) ok = BuildIntraLevels(out);
+  if (ok && defer_tokens_) ok = AttachTokenPartitions(out);  // needs this frame's probabilities
   if (!refresh_entropy) probs_ = saved;
   if (rc != VP8R_OK) return rc;
-  if (!key_frame_ && !BuildIntraLevels(out)) return Fail(VP8R_ERR_NOMEM, "out of host memory");
+  if (!ok) return Fail(VP8R_ERR_NOMEM, "out of host memory");
 
   if (first_.Overrun()) return Fail(VP8R_ERR_TRUNCATED, "first partition read past its end");
   for (int i = 0; i < n_dct_parts_; ++i)

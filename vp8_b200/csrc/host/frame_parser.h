@@ -33,6 +33,9 @@ class FrameParser {
   // Returns a vp8r_status; on failure `error()` describes it.
   int Parse(const uint8_t *data, size_t size, vp8r_frame *out);
   const std::string &error() const { return error_; }
+  // Deferred tokens: parse the first partition only and attach the DCT partitions to the frame for
+  // the device-side token decoder (vp8r_frame_hdr.tokens_deferred).  Survives Reset().
+  void set_defer_tokens(bool on) { defer_tokens_ = on; }
 
  private:
   struct Mv {
@@ -73,6 +76,7 @@ class FrameParser {
                      bool *nz_after_dequant);
   bool EnsurePayload(vp8r_frame *out, size_t blocks_needed);
   bool BuildIntraLevels(vp8r_frame *out);
+  bool AttachTokenPartitions(vp8r_frame *out);
   static constexpr unsigned kMaxFlatIntraLevels = 48;
 
   // ---- state that persists between frames (ParserContext, src/bitstream_parser.h:124-182) ----
@@ -88,7 +92,10 @@ class FrameParser {
   // ---- per-frame scratch ----
   BoolReader first_;
   BoolReader dct_[8];
+  const uint8_t *dct_data_[8] = {};  // start / size of each DCT partition inside the compressed frame
+  size_t dct_size_[8] = {};
   int n_dct_parts_ = 1;
+  bool defer_tokens_ = false;
   bool key_frame_ = false;
   int version_ = 0;
   bool segmentation_enabled_ = false, update_segment_map_ = false;

@@ -108,6 +108,8 @@ struct vp8r_engine {
   // host-visible fences (vp8r_engine_fence / vp8r_engine_wait)
   cudaEvent_t fence_ev[16] = {};
   uint64_t fence_head = 0;
+  // device-visible error word written by K_tokens (mapped pinned host memory)
+  int *h_status = nullptr, *d_status = nullptr;
   // timing
   bool timing = false;
   std::vector<EventPair> live;
@@ -231,6 +233,7 @@ void DrainTimers(vp8r_engine *e) {
         case 1: e->acc.ms_intra += ms; break;
         case 2: e->acc.ms_filter += ms; break;
         case 3: e->acc.ms_h2d += ms; break;
+        case 5: e->acc.ms_tokens += ms; break;
         default: e->acc.ms_d2h += ms; break;
       }
     } else {
@@ -295,6 +298,14 @@ VP8R_API int vp8r_engine_create(int device, void *cuda_stream, vp8r_engine **out
     e->own_stream = true;
   }
   for (auto &sl : e->slots) cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+  if (cudaHostAlloc(reinterpret_cast<void **>(&e->h_status), sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer(reinterpret_cast<void **>(&e->d_status), e->h_status, 0) != cudaSuccess) {
+    cudaGetLastError();
+    SetError("cudaHostAlloc(status word) failed");
+    vp8r_engine_destroy(e);
+    return VP8R_ERR_CUDA;
+  }
+  *e->h_status = 0;
   err = vp8r::InitKernelTables();
   if (err != cudaSuccess) {
     SetError(std::string("kernel table upload: ") + cudaGetErrorString(err));
@@ -321,6 +332,7 @@ VP8R_API void vp8r_engine_destroy(vp8r_engine *e) {
   if (e->d_sums) cudaFree(e->d_sums);
   if (e->d_sync) cudaFree(e->d_sync);
   if (e->d_pack) cudaFree(e->d_pack);
+  if (e->h_status) cudaFreeHost(e->h_status);
   for (auto &ev : e->fence_ev)
     if (ev) cudaEventDestroy(ev);
   DrainTimers(e);
@@ -336,6 +348,11 @@ VP8R_API int vp8r_engine_sync(vp8r_engine *e) {
   if (!e) return VP8R_ERR_INVALID_ARG;
   CU_TRY(cudaStreamSynchronize(e->st));
   for (auto &sl : e->slots) sl.pending = false;
+  if (e->h_status && *static_cast<volatile int *>(e->h_status) != 0) {
+    *e->h_status = 0;
+    SetError("DCT partition read past its end (device token decoder)");
+    return VP8R_ERR_TRUNCATED;
+  }
   return VP8R_OK;
 }
 
@@ -364,7 +381,8 @@ VP8R_API int vp8r_frame_upload(vp8r_engine *e, vp8r_frame *f) {
   f->DropDeviceCopy();
   size_t bytes = f->used_bytes();
   void *p = nullptr;
-  cudaError_t err = cudaMalloc(&p, bytes + 64);
+  const size_t coef_area = f->hdr.tokens_deferred ? vp8r::TokenCoefBlocks(f->hdr.mb_cols, f->hdr.mb_rows) * 32 : 0;
+  cudaError_t err = cudaMalloc(&p, ((bytes + 255) & ~size_t(255)) + coef_area + 64);
   if (err != cudaSuccess) {
     SetError(std::string("cudaMalloc(frame): ") + cudaGetErrorString(err));
     return VP8R_ERR_NOMEM;
@@ -404,7 +422,10 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
       SetError("inter frame without matching reference frames");
       return VP8R_ERR_STATE;
     }
-    if (!(f->d_blob && f->d_device == e->device)) arena += (f->used_bytes() + 255) & ~size_t(255);
+    if (!(f->d_blob && f->d_device == e->device)) {
+      arena += (f->used_bytes() + 255) & ~size_t(255);
+      if (h.tokens_deferred) arena += vp8r::TokenCoefBlocks(h.mb_cols, h.mb_rows) * 32;
+    }
   }
   Slot &sl = e->slots[e->cur_slot];
   e->cur_slot ^= 1;
@@ -416,8 +437,8 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
   if (rc) return rc;
 
   // Pass 2: jobs + host->device staging.
-  int max_mbs = 0, max_rows = 0;
-  bool any_inter = false, any_intra = false, any_wave = false;
+  int max_mbs = 0, max_rows = 0, max_cols = 0;
+  bool any_inter = false, any_intra = false, any_wave = false, any_tokens = false;
   std::vector<int> level_max;  // per dependency level: most intra MBs of that level in any frame
   size_t at = 0;
   std::vector<int> cur_idx(n);
@@ -443,6 +464,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
         CU_TRY(cudaMemcpyAsync(dst, f->blob, f->used_bytes(), cudaMemcpyHostToDevice, e->st));
         dev_blob = dst;
         at += (f->used_bytes() + 255) & ~size_t(255);
+        if (h.tokens_deferred) at += vp8r::TokenCoefBlocks(h.mb_cols, h.mb_rows) * 32;
       }
       j.mbs = reinterpret_cast<const vp8r_mb_info *>(dev_blob);
       j.payload = reinterpret_cast<const int16_t *>(dev_blob + f->mb_bytes());
@@ -457,6 +479,14 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
         for (uint32_t L = 0; L < h.n_intra_levels; ++L) level_max[L] = std::max(level_max[L], int(tab[L + 1] - tab[L]));
       } else if (j.n_intra > 0) {
         any_wave = true;
+      }
+      if (h.tokens_deferred) {
+        // coefficient area: right behind the (256-byte aligned) blob, same allocation
+        j.tok_hdr = reinterpret_cast<const uint8_t *>(j.payload + size_t(h.tokens_at) * 16);
+        j.coef_base = uint32_t((((f->used_bytes() + 255) & ~size_t(255)) - f->mb_bytes()) / 32);
+        j.status = e->d_status;
+        any_tokens = true;
+        max_cols = std::max(max_cols, int(h.mb_cols));
       }
       std::memcpy(j.dq, h.dq, sizeof(j.dq));
       j.key_frame = h.key_frame;
@@ -475,6 +505,11 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
     CU_TRY(cudaMemcpyAsync(sl.d_jobs, sl.h_jobs, sizeof(DevFrameJob) * n, cudaMemcpyHostToDevice, e->st));
   }
 
+  if (any_tokens) {
+    ScopedTimer t(e, 5);
+    CU_TRY(vp8r::LaunchTokens(sl.d_jobs, n, max_cols, e->st));
+    e->acc.launches_other++;
+  }
   if (any_inter) {
     ScopedTimer t(e, 0);
     CU_TRY(vp8r::LaunchInter(sl.d_jobs, n, max_mbs, e->st));

@@ -52,6 +52,11 @@ class Parser:
     def reset(self):
         self._lib.vp8r_parser_reset(self.handle)
 
+    def set_defer_tokens(self, on=True):
+        """First partition only on the host; the DCT partitions travel with the frame and are
+        decoded by the engine's token kernel (vp8r_frame_hdr.tokens_deferred)."""
+        self._lib.vp8r_parser_set_defer_tokens(self.handle, 1 if on else 0)
+
     def close(self):
         if self.handle:
             self._lib.vp8r_parser_destroy(self.handle)
