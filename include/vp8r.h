@@ -97,7 +97,8 @@ typedef struct vp8r_frame_hdr {
   uint8_t refresh_last, refresh_golden, refresh_altref; /* key frames: all 1 */
   uint8_t copy_to_golden, copy_to_altref;               /* 0 none, 1 last, 2 other (loop.h:19-46) */
   uint8_t sign_bias_golden, sign_bias_altref;
-  uint8_t reserved0[2];
+  uint8_t reserved0[1];
+  uint8_t modes_deferred;     /* 1: see modes_at below (implies tokens_deferred) */
   uint8_t tokens_deferred;    /* 1: see tokens_at below */
   int16_t dq[4][6];           /* dequant factors per segment (row 0 only when segmentation is off) */
   uint32_t n_coef_blocks;     /* coefficient blocks stored in payload[] */
@@ -117,7 +118,36 @@ typedef struct vp8r_frame_hdr {
    * DCT partitions; the engine's token kernel (one thread per partition, rows pipelined through
    * the above-context as in src/bitstream_parser.cc:466-537) fills the rest on the device. */
   uint32_t tokens_at;
+  /* Deferred modes (vp8r_parser_set_defer_modes): the host parsed the frame header only (tag, segment /
+   * filter / quantiser headers, probability updates).  There are NO host vp8r_mb_info records
+   * (vp8r_frame_desc.mbs is empty); the payload carries a vp8r_mode_hdr at block `modes_at`, the
+   * vp8r_token_hdr at `tokens_at`, and the raw bytes of the first partition and the DCT partitions.
+   * The engine's parse kernel reads the per-macroblock syntax (src/bitstream_parser.cc:320-464,
+   * src/inter_predict.cc:8-244, src/intra_predict.cc:176-183) on the device, one thread per frame,
+   * running ahead of the token threads, and builds the intra dependency levels there too. */
+  uint32_t modes_at;
 } vp8r_frame_hdr;
+
+/* Per-frame parser state handed to the device-side macroblock-header decoder (160 bytes). */
+typedef struct vp8r_mode_hdr {
+  uint32_t first_off;   /* byte offset of the first partition inside the raw section (4-byte aligned) */
+  uint32_t first_size;  /* bytes */
+  uint32_t bitpos;      /* bit index, from the start of the first partition, of the first stream bit
+                           behind the 8 bits held in `value` (bool decoder hand-over after the headers) */
+  uint8_t value, range; /* bool decoder state: top 8 bits of the window, current range (128..255) */
+  uint8_t key_frame, segmentation_enabled, update_segment_map, mb_no_skip_coeff;
+  uint8_t prob_skip_false, prob_intra, prob_last, prob_gf;
+  uint8_t sign_bias[4];            /* by reference frame id; [2] golden, [3] altref */
+  uint8_t segment_tree_probs[3];
+  uint8_t segment_abs;
+  int8_t segment_lf[4];
+  uint8_t lf_adj_enable, frame_lf_level;
+  int8_t ref_lf_delta[4], mode_lf_delta[4];
+  uint8_t ymode_probs[4], uvmode_probs[3];
+  uint8_t pad0;
+  uint8_t mv_probs[2][19];
+  uint8_t pad1[160 - 12 - 10 - 4 - 4 - 4 - 2 - 8 - 8 - 38];
+} vp8r_mode_hdr;
 
 /* Header of the deferred-token section of the payload (32-byte aligned, 1152 bytes). */
 typedef struct vp8r_token_hdr {
@@ -162,6 +192,13 @@ VP8R_API int vp8r_frame_get_desc(const vp8r_frame *f, vp8r_frame_desc *out);
  * vp8r_frame_hdr.tokens_at.  Over-reads of a DCT partition are then reported by
  * vp8r_engine_sync() instead of the parse call. */
 VP8R_API void vp8r_parser_set_defer_tokens(vp8r_parser *p, int on);
+
+/* on != 0: later vp8r_parser_parse calls read the frame header only; the per-macroblock syntax of the
+ * first partition and the DCT partitions are decoded by the engine's parse kernel (implies deferred
+ * tokens; see vp8r_frame_hdr.modes_at).  The stream's segment map then lives on the device, so a
+ * stream must not switch this mode between key frames.  Over-reads of the first partition are
+ * reported by vp8r_engine_sync(). */
+VP8R_API void vp8r_parser_set_defer_modes(vp8r_parser *p, int on);
 
 /* Parses one compressed frame (the payload of one IVF frame record) into `out`. */
 VP8R_API int vp8r_parser_parse(vp8r_parser *p, const uint8_t *data, size_t size, vp8r_frame *out);

@@ -24,7 +24,7 @@ def test_header_and_library_agree(built):
 def test_struct_layout(built):
     from vp8_b200 import _capi
     assert C.sizeof(_capi.MbInfo) == 32
-    assert C.sizeof(_capi.FrameHdr) == 8 + 16 + 48 + 28
+    assert C.sizeof(_capi.FrameHdr) == 8 + 16 + 48 + 32
     assert C.sizeof(_capi.TokenHdr) == 1152
 
 

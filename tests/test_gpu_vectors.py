@@ -299,18 +299,21 @@ def test_packed_readback_equals_pitched_readback(engine):
 
 
 # ---- device-side token decode (deferred tokens) ----------------------------------
-def _decode_deferred(engine, payloads):
-    """All frames of one stream with the DCT partitions decoded on the device; returns the I420 of
-    every frame (shown or not) and the show flags."""
+def _decode_deferred(engine, payloads, modes=False):
+    """All frames of one stream with the DCT partitions (and, with `modes`, the macroblock headers of
+    the first partition) decoded on the device; returns the I420 of every frame (shown or not) and
+    the show flags."""
     import vp8_b200
     ps = vp8_b200.Parser()
     ps.set_defer_tokens(True)
+    if modes:
+        ps.set_defer_modes(True)
     st = engine.open_stream()
     out, shown = [], []
     try:
         for p in payloads:
             fr = ps.parse(p, pinned=True)
-            assert fr.desc().hdr.tokens_deferred == 1
+            assert fr.desc().hdr.tokens_deferred == 1 and fr.desc().hdr.modes_deferred == int(modes)
             engine.reconstruct_batch([st], [fr])
             engine.sync()
             out.append(st.read_frame())
@@ -322,14 +325,16 @@ def _decode_deferred(engine, payloads):
     return out, shown
 
 
+@pytest.mark.parametrize("modes", [False, True], ids=["tokens", "modes+tokens"])
 @pytest.mark.parametrize("ivf", helpers.vectors(), ids=lambda p: os.path.basename(p)[:-4])
-def test_device_tokens_match_golden_and_oracle(engine, ivf):
-    """Host parses the first partition only; K_tokens decodes the DCT partitions.  Every frame byte
-    for byte against host parser -> oracle, shown frames against the golden MD5s."""
+def test_device_tokens_match_golden_and_oracle(engine, ivf, modes):
+    """Host parses the first partition only (or, with `modes`, just the frame header); the parse kernel
+    decodes the rest.  Every frame byte for byte against host parser -> oracle, shown frames against
+    the golden MD5s."""
     import vp8_b200
     gold = helpers.golden_md5(ivf)
     _, payloads = vp8_b200.read_ivf(ivf)
-    got, shown = _decode_deferred(engine, payloads)
+    got, shown = _decode_deferred(engine, payloads, modes)
     ps, orc = vp8_b200.Parser(), helpers.Oracle()
     k_shown = 0
     for k, p in enumerate(payloads):
@@ -345,13 +350,14 @@ def test_device_tokens_match_golden_and_oracle(engine, ivf):
     orc.close()
 
 
+@pytest.mark.parametrize("modes", [False, True], ids=["tokens", "modes+tokens"])
 @pytest.mark.parametrize("name", sorted(helpers.synth_manifest().keys()))
-def test_device_tokens_synthetic_streams(engine, name):
+def test_device_tokens_synthetic_streams(engine, name, modes):
     """Same, on the synthetic streams (1/2/4/8 DCT partitions, segment quantisers, 1080p)."""
     import vp8_b200
     m = helpers.synth_manifest()[name]
     _, payloads = vp8_b200.read_ivf(helpers.synth_stream(m["args"]))
-    got, shown = _decode_deferred(engine, payloads)
+    got, shown = _decode_deferred(engine, payloads, modes)
     gold = helpers.synth_golden(name)
     imgs = [g for g, s in zip(got, shown) if s]
     assert len(imgs) == len(gold)
@@ -367,13 +373,13 @@ def test_device_tokens_batched_and_truncated(engine):
     ivfs = [helpers.synth_stream(f"--width 320 --height 192 --frames 5 --seed {70 + k} --log2-parts {k % 4}") for k in range(6)]
     payloads = [vp8_b200.read_ivf(d)[1] for d in ivfs]
     sums = []
-    for dev in (False, True):
-        dec = vp8_b200.BatchDecoder(engine, len(ivfs), pinned=True, tokens_on_device=dev)
+    for tok, par in ((False, False), (True, False), (False, True)):
+        dec = vp8_b200.BatchDecoder(engine, len(ivfs), pinned=True, tokens_on_device=tok, device_parse=par)
         per_step = []
         dec.decode(payloads, on_step=lambda t, live, frames: per_step.append(engine.checksum_batch([dec.streams[i] for i in live])))
         sums.append(per_step)
         dec.close()
-    assert sums[0] == sums[1]
+    assert sums[0] == sums[1] == sums[2]
     # cut the tail of the last partition of a frame with many tokens: the token kernel must flag it
     ps = vp8_b200.Parser()
     ps.set_defer_tokens(True)

@@ -17,12 +17,12 @@ class FrameHdr(C.Structure):
                 ("filter_type", C.c_uint8), ("loop_filter_level", C.c_uint8), ("sharpness_level", C.c_uint8),
                 ("refresh_last", C.c_uint8), ("refresh_golden", C.c_uint8), ("refresh_altref", C.c_uint8),
                 ("copy_to_golden", C.c_uint8), ("copy_to_altref", C.c_uint8),
-                ("sign_bias_golden", C.c_uint8), ("sign_bias_altref", C.c_uint8), ("reserved0", C.c_uint8 * 2),
-                ("tokens_deferred", C.c_uint8),
+                ("sign_bias_golden", C.c_uint8), ("sign_bias_altref", C.c_uint8), ("reserved0", C.c_uint8 * 1),
+                ("modes_deferred", C.c_uint8), ("tokens_deferred", C.c_uint8),
                 ("dq", (C.c_int16 * 6) * 4),
                 ("n_coef_blocks", C.c_uint32), ("n_payload_blocks", C.c_uint32),
                 ("n_inter_mbs", C.c_uint32), ("n_split_mbs", C.c_uint32),
-                ("n_intra_levels", C.c_uint32), ("intra_levels_at", C.c_uint32), ("tokens_at", C.c_uint32)]
+                ("n_intra_levels", C.c_uint32), ("intra_levels_at", C.c_uint32), ("tokens_at", C.c_uint32), ("modes_at", C.c_uint32)]
 
 
 class TokenHdr(C.Structure):
@@ -48,6 +48,7 @@ SIGNATURES = {
     "vp8r_parser_destroy": (None, [C.c_void_p]),
     "vp8r_parser_reset": (None, [C.c_void_p]),
     "vp8r_parser_set_defer_tokens": (None, [C.c_void_p, C.c_int]),
+    "vp8r_parser_set_defer_modes": (None, [C.c_void_p, C.c_int]),
     "vp8r_frame_create": (C.c_void_p, [C.c_int]),
     "vp8r_frame_destroy": (None, [C.c_void_p]),
     "vp8r_frame_get_desc": (C.c_int, [C.c_void_p, C.POINTER(FrameDesc)]),

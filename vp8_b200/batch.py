@@ -14,16 +14,20 @@ from .decoder import ParsedFrame, Parser
 
 
 class BatchDecoder:
-    def __init__(self, engine, n_streams, parse_threads=None, pinned=True, tokens_on_device=False):
+    def __init__(self, engine, n_streams, parse_threads=None, pinned=True, tokens_on_device=False, device_parse=False):
         self.engine = engine
         self._lib = engine._lib
         self.n = n_streams
         self.parse_threads = parse_threads or min(n_streams, os.cpu_count() or 1)
         self.parsers = [Parser() for _ in range(n_streams)]
         self.tokens_on_device = tokens_on_device
+        self.device_parse = device_parse
         if tokens_on_device:  # host: headers, modes, motion vectors; device: DCT token partitions
             for p in self.parsers:
                 p.set_defer_tokens(True)
+        if device_parse:      # host: frame headers only; device: all per-macroblock syntax
+            for p in self.parsers:
+                p.set_defer_modes(True)
         self.streams = [engine.open_stream() for _ in range(n_streams)]
         self.slots = [[ParsedFrame(pinned=pinned) for _ in range(n_streams)] for _ in range(2)]
 
@@ -81,7 +85,7 @@ class BatchDecoder:
             decoded += len(live)
             for f in frames:
                 d = f.desc()
-                h2d += d.hdr.mb_cols * d.hdr.mb_rows * 32 + d.hdr.n_payload_blocks * 32
+                h2d += (0 if d.hdr.modes_deferred else d.hdr.mb_cols * d.hdr.mb_rows * 32) + d.hdr.n_payload_blocks * 32
                 shown += d.hdr.show_frame
             if out_ring is not None:
                 ring = out_ring[t & 1]

@@ -35,6 +35,10 @@ VP8R_API void vp8r_parser_set_defer_tokens(vp8r_parser *p, int on) {
   if (p) p->impl.set_defer_tokens(on != 0);
 }
 
+VP8R_API void vp8r_parser_set_defer_modes(vp8r_parser *p, int on) {
+  if (p) p->impl.set_defer_modes(on != 0);
+}
+
 VP8R_API vp8r_frame *vp8r_frame_create(int pinned) {
   vp8r_frame *f = new (std::nothrow) vp8r_frame();
   if (f) f->pinned = pinned != 0;

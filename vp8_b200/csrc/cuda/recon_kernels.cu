@@ -95,6 +95,8 @@ cudaError_t InitKernelTables() {
   }
   cudaError_t err = cudaMemcpyToSymbol(c_taps, taps, sizeof(taps));
   if (err != cudaSuccess) return err;
+  err = InitParseTables();
+  if (err != cudaSuccess) return err;
   unsigned short lut[160];
   std::memset(lut, 0, sizeof(lut));
   BuildBpredLut(lut);
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(kInterWarps * 32) InterKernel(const DevFrameJo
   const DevFrameJob &job = jobs[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mb_index = blockIdx.x * kInterWarps + warp;
-  if (job.n_inter == 0 || mb_index >= job.mb_cols * job.mb_rows) return;
+  if (JobInter(job) == 0 || mb_index >= job.mb_cols * job.mb_rows) return;
   vp8r_mb_info mb;
   {
     const int4 *p = reinterpret_cast<const int4 *>(job.mbs + mb_index);
@@ -589,7 +591,7 @@ __device__ __forceinline__ void IntraMacroblock(const DevFrameJob &job, int r, i
 __global__ void __launch_bounds__(kWaveWarps * 32) IntraKernel(const DevFrameJob *__restrict__ jobs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const DevFrameJob &job = jobs[blockIdx.x];
-  if (job.n_intra == 0 || job.n_intra_levels != 0) return;
+  if (JobIntra(job) == 0 || JobIntraLevels(job) != 0) return;
   const int rows = job.mb_rows, cols = job.mb_cols;
   volatile int *progress = reinterpret_cast<volatile int *>(smem_raw);
   unsigned short *lut = reinterpret_cast<unsigned short *>(smem_raw + ((rows * 4 + 15) & ~15));
@@ -625,7 +627,7 @@ __global__ void __launch_bounds__(kFlatWarps * 32) IntraFlatKernel(const DevFram
   __shared__ __align__(16) unsigned short lut[160];
   __shared__ IntraScratch scratch[kFlatWarps];
   const DevFrameJob &job = jobs[blockIdx.y];
-  if (level >= job.n_intra_levels) return;
+  if (job.dyn || level >= job.n_intra_levels) return;  // device-built tables: IntraLevelsKernel
   const unsigned first = __ldg(job.intra_levels + level), end = __ldg(job.intra_levels + level + 1);
   for (int i = threadIdx.x; i < 160; i += blockDim.x) lut[i] = c_bpred_lut[i];
   __syncthreads();
@@ -635,6 +637,38 @@ __global__ void __launch_bounds__(kFlatWarps * 32) IntraFlatKernel(const DevFram
   const unsigned mb_index = __ldg(job.intra_levels + job.n_intra_levels + 1 + slot);
   const int r = mb_index / job.mb_cols, c = mb_index - r * job.mb_cols;
   IntraMacroblock(job, r, c, lane, scratch[warp], lut, nullptr);
+}
+
+// Frames whose level table was built on the device (deferred modes): the host does not know how many
+// levels or macroblocks per level there are, so one CTA per frame walks all levels, its warps sharing
+// the macroblocks of a level, with a block barrier between levels.
+constexpr int kLevelWarps = 16;
+__global__ void __launch_bounds__(kLevelWarps * 32) IntraLevelsKernel(const DevFrameJob *__restrict__ jobs) {
+  __shared__ __align__(16) unsigned short lut[160];
+  __shared__ IntraScratch scratch[kLevelWarps];
+  const DevFrameJob &job = jobs[blockIdx.x];
+  if (!job.dyn) return;
+  const int n_levels = job.dyn->n_intra_levels;
+  if (n_levels == 0) return;
+  for (int i = threadIdx.x; i < 160; i += blockDim.x) lut[i] = c_bpred_lut[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t *tab = job.level_table;
+  const uint32_t *order = tab + n_levels + 1;
+  for (int level = 0; level < n_levels; ++level) {
+    const unsigned first = tab[level], end = tab[level + 1];
+    for (unsigned slot = first + warp; slot < end; slot += kLevelWarps) {
+      const unsigned mb_index = order[slot];
+      const int r = mb_index / job.mb_cols, c = mb_index - r * job.mb_cols;
+      IntraMacroblock(job, r, c, lane, scratch[warp], lut, nullptr);
+    }
+    __syncthreads();  // pixels of this level are visible to the whole CTA before the next starts
+  }
+}
+
+cudaError_t LaunchIntraLevels(const DevFrameJob *jobs, int n_frames, cudaStream_t st) {
+  IntraLevelsKernel<<<n_frames, kLevelWarps * 32, 0, st>>>(jobs);
+  return cudaGetLastError();
 }
 
 cudaError_t LaunchIntraFlat(const DevFrameJob *jobs, int n_frames, int level, int max_count, cudaStream_t st) {

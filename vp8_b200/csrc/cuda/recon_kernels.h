@@ -18,6 +18,12 @@ struct DevPlanes {
   uint8_t *y, *u, *v;  // address of pixel (0,0) of each plane
 };
 
+// Per-frame results of the device-side macroblock-header pass (frames with deferred modes): what the
+// host parser would have put into vp8r_frame_hdr.
+struct DevFrameDyn {
+  int n_inter, n_intra, n_intra_levels, n_split;
+};
+
 // One frame of one stream inside a batched launch.
 struct DevFrameJob {
   const vp8r_mb_info *mbs;
@@ -40,14 +46,34 @@ struct DevFrameJob {
   // and the frame's device coefficient area (first block index relative to `payload`)
   const uint8_t *tok_hdr;
   uint32_t coef_base;
-  int *status;                   // device-visible error word (bit 0: a DCT partition was over-read)
+  int *status;                   // device-visible error word (bit 0: a DCT partition was over-read,
+                                 // bit 1: the first partition was)
+  // deferred modes: vp8r_mode_hdr inside the payload; `mbs` then points at a device area the parse
+  // kernel fills, as are the SPLIT motion vectors (first block index relative to `payload`), the
+  // intra level table and `dyn`; the segment map persists per stream
+  const uint8_t *mode_hdr;
+  uint32_t split_base;
+  uint8_t *segment_map;
+  uint32_t *level_table;
+  DevFrameDyn *dyn;
 };
+
+// Frame fields that come from the host for host-parsed frames and from the device otherwise.
+__device__ __forceinline__ int JobInter(const DevFrameJob &j) { return j.dyn ? j.dyn->n_inter : j.n_inter; }
+__device__ __forceinline__ int JobIntra(const DevFrameJob &j) { return j.dyn ? j.dyn->n_intra : j.n_intra; }
+__device__ __forceinline__ int JobIntraLevels(const DevFrameJob &j) { return j.dyn ? j.dyn->n_intra_levels : j.n_intra_levels; }
+__device__ __forceinline__ const uint32_t *JobLevelTable(const DevFrameJob &j) { return j.dyn ? j.level_table : j.intra_levels; }
 
 // Uploads the constant tables (filter taps, B_PRED gather LUT).  Once per device.
 cudaError_t InitKernelTables();
 
 // K_tokens: device-side token decode of every job with tok_hdr != nullptr (see token_kernel.cu).
-cudaError_t LaunchTokens(const DevFrameJob *jobs, int n_frames, int max_cols, cudaStream_t st);
+// `modes`: some job also has mode_hdr (one more working thread per frame, more shared memory).
+cudaError_t LaunchTokens(const DevFrameJob *jobs, int n_frames, int max_cols, int max_mbs, bool modes, cudaStream_t st);
+cudaError_t InitParseTables();
+// Level-scheduled intra prediction of frames whose level table was built on the device: one CTA per
+// frame walks the dependency levels with a block barrier in between.
+cudaError_t LaunchIntraLevels(const DevFrameJob *jobs, int n_frames, cudaStream_t st);
 // Blocks (32 B) of device coefficient area a frame with deferred tokens needs.
 inline size_t TokenCoefBlocks(int mb_cols, int mb_rows) { return size_t(mb_cols) * mb_rows * 25; }
 // K_inter: dequant + IWHT/IDCT + motion compensation + residual add for every inter MB.

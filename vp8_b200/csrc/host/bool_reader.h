@@ -71,6 +71,16 @@ class BoolReader {
     return -i;
   }
 
+  // Hand-over of the decoder state to another implementation (the device-side decoder): after
+  // Prime(), the window is `Top8()` followed by the raw stream bits from bit `Shifts() + 8` on
+  // (subtractions only ever touch the top 8 bits, so everything below them is still raw stream).
+  void Prime() {
+    if (avail_ < 8) Refill();
+  }
+  uint32_t Top8() const { return uint32_t(window_ >> 56); }
+  uint32_t Range() const { return range_; }
+  size_t Shifts() const { return 8 * loaded_ - size_t(avail_); }
+
   // Bytes the reference's byte-at-a-time reader would have consumed so far.
   size_t BytesConsumed() const { return 2 + ((8 * loaded_ - size_t(avail_)) >> 3); }
   bool Overrun() const { return used_ && BytesConsumed() > size_; }

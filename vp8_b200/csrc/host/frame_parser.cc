@@ -147,6 +147,8 @@ int FrameParser::ParseHeader(const uint8_t *data, size_t size, vp8r_frame *out) 
   if (tag_size + first_size >= size) return Fail(VP8R_ERR_TRUNCATED, "first partition exceeds the frame");
   first_.Init(data + tag_size, first_size);
   first_.MarkUsed();
+  first_data_ = data + tag_size;
+  first_size_ = first_size;
   BoolReader &br = first_;
 
   if (key_frame_) {
@@ -689,30 +691,73 @@ bool FrameParser::BuildIntraLevels(vp8r_frame *out) {
 bool FrameParser::AttachTokenPartitions(vp8r_frame *out) {
   vp8r_frame_hdr &h = out->hdr;
   static_assert(sizeof(vp8r_token_hdr) == 1152, "vp8r_token_hdr layout");
+  static_assert(sizeof(vp8r_mode_hdr) == 160, "vp8r_mode_hdr layout");
   size_t raw = 0;
   for (int i = 0; i < n_dct_parts_; ++i) raw += (dct_size_[i] + 3) & ~size_t(3);
+  const size_t first_at = raw;
+  if (defer_modes_) raw += (first_size_ + 3) & ~size_t(3);
   const size_t raw_padded = (raw + 16 + 31) & ~size_t(31);
-  const size_t blocks = (sizeof(vp8r_token_hdr) + raw_padded) / 32;
+  const size_t mode_bytes = defer_modes_ ? sizeof(vp8r_mode_hdr) : 0;
+  const size_t blocks = (mode_bytes + sizeof(vp8r_token_hdr) + raw_padded) / 32;
   if (!EnsurePayload(out, size_t(h.n_payload_blocks) + blocks)) return false;
   uint8_t *base = reinterpret_cast<uint8_t *>(out->payload() + size_t(h.n_payload_blocks) * 16);
-  vp8r_token_hdr *th = reinterpret_cast<vp8r_token_hdr *>(base);
+  vp8r_token_hdr *th = reinterpret_cast<vp8r_token_hdr *>(base + mode_bytes);
   std::memset(th, 0, 96);
   th->n_parts = uint32_t(n_dct_parts_);
-  uint8_t *dst = base + sizeof(vp8r_token_hdr);
+  uint8_t *dst = reinterpret_cast<uint8_t *>(th) + sizeof(vp8r_token_hdr);
   size_t at = 0;
+  auto put = [&](const uint8_t *src, size_t n) {
+    if (n) std::memcpy(dst + at, src, n);
+    size_t end = at + n;
+    at = (end + 3) & ~size_t(3);
+    std::memset(dst + end, 0, at - end);
+  };
   for (int i = 0; i < n_dct_parts_; ++i) {
     th->part_off[i] = uint32_t(at);
     th->part_size[i] = uint32_t(dct_size_[i]);
-    if (dct_size_[i]) std::memcpy(dst + at, dct_data_[i], dct_size_[i]);
-    size_t end = at + dct_size_[i];
-    at = (end + 3) & ~size_t(3);
-    std::memset(dst + end, 0, at - end);
+    put(dct_data_[i], dct_size_[i]);
   }
+  if (defer_modes_) put(first_data_, first_size_);
   std::memset(dst + at, 0, raw_padded - at);
   th->raw_bytes = uint32_t(raw_padded);
   std::memcpy(th->coef_probs, probs_.coef, sizeof(th->coef_probs));
   h.tokens_deferred = 1;
-  h.tokens_at = h.n_payload_blocks;
+  h.tokens_at = h.n_payload_blocks + uint32_t(mode_bytes / 32);
+  if (defer_modes_) {
+    vp8r_mode_hdr *mh = reinterpret_cast<vp8r_mode_hdr *>(base);
+    std::memset(mh, 0, sizeof(*mh));
+    first_.Prime();
+    mh->first_off = uint32_t(first_at);
+    mh->first_size = uint32_t(first_size_);
+    mh->bitpos = uint32_t(first_.Shifts() + 8);
+    mh->value = uint8_t(first_.Top8());
+    mh->range = uint8_t(first_.Range());
+    mh->key_frame = key_frame_;
+    mh->segmentation_enabled = segmentation_enabled_;
+    mh->update_segment_map = update_segment_map_;
+    mh->mb_no_skip_coeff = mb_no_skip_coeff_;
+    mh->prob_skip_false = uint8_t(prob_skip_false_);
+    mh->prob_intra = uint8_t(prob_intra_);
+    mh->prob_last = uint8_t(prob_last_);
+    mh->prob_gf = uint8_t(prob_gf_);
+    for (int i = 0; i < 4; ++i) {
+      mh->sign_bias[i] = sign_bias_[i];
+      mh->segment_lf[i] = int8_t(segment_lf_[i]);
+      mh->ref_lf_delta[i] = ref_lf_delta_[i];
+      mh->mode_lf_delta[i] = mode_lf_delta_[i];
+      mh->ymode_probs[i] = probs_.ymode[i];
+    }
+    for (int i = 0; i < 3; ++i) {
+      mh->segment_tree_probs[i] = segment_tree_probs_[i];
+      mh->uvmode_probs[i] = probs_.uvmode[i];
+    }
+    mh->segment_abs = uint8_t(segment_abs_);
+    mh->lf_adj_enable = lf_adj_enable_;
+    mh->frame_lf_level = uint8_t(frame_lf_level_);
+    std::memcpy(mh->mv_probs, probs_.mv, sizeof(mh->mv_probs));
+    h.modes_deferred = 1;
+    h.modes_at = h.n_payload_blocks;
+  }
   h.n_payload_blocks += uint32_t(blocks);
   return true;
 }
@@ -754,9 +799,14 @@ int FrameParser::Parse(const uint8_t *data, size_t size, vp8r_frame *out) {
         }
   }
 
-  out->n_mb = size_t(mb_cols_) * mb_rows_;
+  out->n_mb = defer_modes_ ? 0 : size_t(mb_cols_) * mb_rows_;  // deferred modes: no host MB records
   out->hdr.n_coef_blocks = out->hdr.n_payload_blocks = 0;
   if (!out->Reserve(out->mb_bytes() + 64 * 1024, 0)) return Fail(VP8R_ERR_NOMEM, "out of host memory");
+  if (defer_modes_) {
+    const bool ok = AttachTokenPartitions(out);
+    if (!refresh_entropy) probs_ = saved;
+    return ok ? int(VP8R_OK) : Fail(VP8R_ERR_NOMEM, "out of host memory");
+  }
 
   rc = ParseMacroblocks(out);
   bool ok = rc == VP8R_OK;

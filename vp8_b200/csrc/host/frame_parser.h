@@ -36,6 +36,9 @@ class FrameParser {
   // Deferred tokens: parse the first partition only and attach the DCT partitions to the frame for
   // the device-side token decoder (vp8r_frame_hdr.tokens_deferred).  Survives Reset().
   void set_defer_tokens(bool on) { defer_tokens_ = on; }
+  // Deferred modes: parse the frame header only; the per-macroblock syntax is decoded on the device
+  // too (vp8r_frame_hdr.modes_deferred).  Implies deferred tokens.
+  void set_defer_modes(bool on) { defer_modes_ = on; }
 
  private:
   struct Mv {
@@ -96,6 +99,9 @@ class FrameParser {
   size_t dct_size_[8] = {};
   int n_dct_parts_ = 1;
   bool defer_tokens_ = false;
+  bool defer_modes_ = false;
+  const uint8_t *first_data_ = nullptr;  // first partition inside the compressed frame
+  size_t first_size_ = 0;
   bool key_frame_ = false;
   int version_ = 0;
   bool segmentation_enabled_ = false, update_segment_map_ = false;

@@ -69,6 +69,7 @@ struct vp8r_stream {
   int mb_cols = 0, mb_rows = 0, width = 0, height = 0;
   int pitch_y = 0, pitch_c = 0;
   vp8r::Surface surf[5];
+  uint8_t *d_segmap = nullptr;  // persistent segment map (frames with deferred modes), one byte per MB
   int ref[4] = {-1, -1, -1, -1};  // surface index of CURRENT(latest), LAST, GOLDEN, ALTREF
   bool have_frame = false;
 };
@@ -97,9 +98,15 @@ struct vp8r_engine {
   // ticket + per-(frame, band) progress words of the wavefront kernels
   int *d_sync = nullptr;
   int sync_cap = 0;
-  // device staging of packed I420 frames (vp8r_read_batch_packed)
+  // device staging of packed I420 frames (vp8r_read_batch_packed): two halves, so that the D2H
+  // copy of one time step (on st_copy) overlaps the kernels of the next (on st)
   uint8_t *d_pack = nullptr;
-  size_t pack_cap = 0;
+  size_t pack_cap = 0;  // bytes per half
+  cudaStream_t st_copy = nullptr;
+  cudaEvent_t pack_done[2] = {}, copy_done[2] = {};
+  bool copy_busy[2] = {false, false};
+  cudaEvent_t fence_copy_ev[16] = {};
+  bool fence_has_copy[16] = {};
   // checksum scratch
   DevFrameJob *h_cjobs = nullptr, *d_cjobs = nullptr;
   unsigned long long *d_sums = nullptr, *h_sums = nullptr;
@@ -129,6 +136,40 @@ void FreeSurfaces(vp8r_stream *s) {
     if (sf.base) cudaFree(sf.base);
     sf = vp8r::Surface{};
   }
+  if (s->d_segmap) cudaFree(s->d_segmap);
+  s->d_segmap = nullptr;
+}
+
+// Device areas behind a frame's blob that the parse kernel fills (deferred tokens / modes).  All
+// offsets are from the start of the device copy of the blob and multiples of 32 bytes.
+struct DevExtra {
+  size_t mb_off = 0, split_off = 0, coef_off = 0, level_off = 0, dyn_off = 0, total = 0;
+};
+DevExtra FrameDevExtra(const vp8r_frame *f) {
+  DevExtra x;
+  const vp8r_frame_hdr &h = f->hdr;
+  size_t at = (f->used_bytes() + 255) & ~size_t(255);
+  if (!h.tokens_deferred) {
+    x.total = at;
+    return x;
+  }
+  const size_t n_mb = size_t(h.mb_cols) * h.mb_rows;
+  if (h.modes_deferred) {
+    x.mb_off = at;
+    at += n_mb * sizeof(vp8r_mb_info);
+    x.split_off = at;
+    at += n_mb * 64;
+  }
+  x.coef_off = at;
+  at += vp8r::TokenCoefBlocks(h.mb_cols, h.mb_rows) * 32;
+  if (h.modes_deferred) {
+    x.level_off = at;
+    at += ((64 + n_mb) * 4 + 31) & ~size_t(31);
+    x.dyn_off = at;
+    at += 32;
+  }
+  x.total = (at + 255) & ~size_t(255);
+  return x;
 }
 
 // (Re)allocates the stream's surface pool for a new frame size (key frames only; the reference
@@ -159,6 +200,16 @@ int ConfigureStream(vp8r_stream *s, const vp8r_frame_hdr &h) {
     sf.planes.y = sf.base + size_t(B) * s->pitch_y + B;
     sf.planes.u = sf.base + ysz + size_t(B) * s->pitch_c + B;
     sf.planes.v = sf.base + ysz + csz + size_t(B) * s->pitch_c + B;
+  }
+  {
+    const size_t n_mb = size_t(h.mb_cols) * h.mb_rows;
+    void *p = nullptr;
+    if (cudaMalloc(&p, n_mb + 256) != cudaSuccess) {
+      SetError("cudaMalloc(segment map) failed");
+      return VP8R_ERR_NOMEM;
+    }
+    s->d_segmap = static_cast<uint8_t *>(p);
+    CU_TRY(cudaMemsetAsync(p, 0, n_mb + 256, s->eng->st));
   }
   s->mb_cols = h.mb_cols;
   s->mb_rows = h.mb_rows;
@@ -298,6 +349,11 @@ VP8R_API int vp8r_engine_create(int device, void *cuda_stream, vp8r_engine **out
     e->own_stream = true;
   }
   for (auto &sl : e->slots) cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+  cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking);
+  for (int k = 0; k < 2; ++k) {
+    cudaEventCreateWithFlags(&e->pack_done[k], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->copy_done[k], cudaEventDisableTiming);
+  }
   if (cudaHostAlloc(reinterpret_cast<void **>(&e->h_status), sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
       cudaHostGetDevicePointer(reinterpret_cast<void **>(&e->d_status), e->h_status, 0) != cudaSuccess) {
     cudaGetLastError();
@@ -320,6 +376,16 @@ VP8R_API void vp8r_engine_destroy(vp8r_engine *e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->st);
+  if (e->st_copy) {
+    cudaStreamSynchronize(e->st_copy);
+    cudaStreamDestroy(e->st_copy);
+  }
+  for (int k = 0; k < 2; ++k) {
+    if (e->pack_done[k]) cudaEventDestroy(e->pack_done[k]);
+    if (e->copy_done[k]) cudaEventDestroy(e->copy_done[k]);
+  }
+  for (auto &ev : e->fence_copy_ev)
+    if (ev) cudaEventDestroy(ev);
   for (auto &sl : e->slots) {
     if (sl.h_jobs) cudaFreeHost(sl.h_jobs);
     if (sl.d_jobs) cudaFree(sl.d_jobs);
@@ -347,10 +413,12 @@ VP8R_API void vp8r_engine_destroy(vp8r_engine *e) {
 VP8R_API int vp8r_engine_sync(vp8r_engine *e) {
   if (!e) return VP8R_ERR_INVALID_ARG;
   CU_TRY(cudaStreamSynchronize(e->st));
+  CU_TRY(cudaStreamSynchronize(e->st_copy));
+  e->copy_busy[0] = e->copy_busy[1] = false;
   for (auto &sl : e->slots) sl.pending = false;
   if (e->h_status && *static_cast<volatile int *>(e->h_status) != 0) {
     *e->h_status = 0;
-    SetError("DCT partition read past its end (device token decoder)");
+    SetError("a partition was read past its end (device-side parse)");
     return VP8R_ERR_TRUNCATED;
   }
   return VP8R_OK;
@@ -381,8 +449,7 @@ VP8R_API int vp8r_frame_upload(vp8r_engine *e, vp8r_frame *f) {
   f->DropDeviceCopy();
   size_t bytes = f->used_bytes();
   void *p = nullptr;
-  const size_t coef_area = f->hdr.tokens_deferred ? vp8r::TokenCoefBlocks(f->hdr.mb_cols, f->hdr.mb_rows) * 32 : 0;
-  cudaError_t err = cudaMalloc(&p, ((bytes + 255) & ~size_t(255)) + coef_area + 64);
+  cudaError_t err = cudaMalloc(&p, FrameDevExtra(f).total + 64);
   if (err != cudaSuccess) {
     SetError(std::string("cudaMalloc(frame): ") + cudaGetErrorString(err));
     return VP8R_ERR_NOMEM;
@@ -422,10 +489,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
       SetError("inter frame without matching reference frames");
       return VP8R_ERR_STATE;
     }
-    if (!(f->d_blob && f->d_device == e->device)) {
-      arena += (f->used_bytes() + 255) & ~size_t(255);
-      if (h.tokens_deferred) arena += vp8r::TokenCoefBlocks(h.mb_cols, h.mb_rows) * 32;
-    }
+    if (!(f->d_blob && f->d_device == e->device)) arena += FrameDevExtra(f).total;
   }
   Slot &sl = e->slots[e->cur_slot];
   e->cur_slot ^= 1;
@@ -438,7 +502,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
 
   // Pass 2: jobs + host->device staging.
   int max_mbs = 0, max_rows = 0, max_cols = 0;
-  bool any_inter = false, any_intra = false, any_wave = false, any_tokens = false;
+  bool any_inter = false, any_intra = false, any_wave = false, any_tokens = false, any_modes = false;
   std::vector<int> level_max;  // per dependency level: most intra MBs of that level in any frame
   size_t at = 0;
   std::vector<int> cur_idx(n);
@@ -463,8 +527,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
         uint8_t *dst = sl.d_arena + at;
         CU_TRY(cudaMemcpyAsync(dst, f->blob, f->used_bytes(), cudaMemcpyHostToDevice, e->st));
         dev_blob = dst;
-        at += (f->used_bytes() + 255) & ~size_t(255);
-        if (h.tokens_deferred) at += vp8r::TokenCoefBlocks(h.mb_cols, h.mb_rows) * 32;
+        at += FrameDevExtra(f).total;
       }
       j.mbs = reinterpret_cast<const vp8r_mb_info *>(dev_blob);
       j.payload = reinterpret_cast<const int16_t *>(dev_blob + f->mb_bytes());
@@ -481,12 +544,27 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
         any_wave = true;
       }
       if (h.tokens_deferred) {
-        // coefficient area: right behind the (256-byte aligned) blob, same allocation
+        // device areas right behind the (256-byte aligned) blob, same allocation, so that block
+        // indices relative to `payload` reach them
+        const DevExtra x = FrameDevExtra(f);
+        uint8_t *wr = const_cast<uint8_t *>(dev_blob);
         j.tok_hdr = reinterpret_cast<const uint8_t *>(j.payload + size_t(h.tokens_at) * 16);
-        j.coef_base = uint32_t((((f->used_bytes() + 255) & ~size_t(255)) - f->mb_bytes()) / 32);
+        j.coef_base = uint32_t((x.coef_off - f->mb_bytes()) / 32);
         j.status = e->d_status;
         any_tokens = true;
         max_cols = std::max(max_cols, int(h.mb_cols));
+        if (h.modes_deferred) {
+          j.mode_hdr = reinterpret_cast<const uint8_t *>(j.payload + size_t(h.modes_at) * 16);
+          j.mbs = reinterpret_cast<const vp8r_mb_info *>(wr + x.mb_off);
+          j.split_base = uint32_t((x.split_off - f->mb_bytes()) / 32);
+          j.segment_map = s->d_segmap;
+          j.level_table = reinterpret_cast<uint32_t *>(wr + x.level_off);
+          j.dyn = reinterpret_cast<vp8r::DevFrameDyn *>(wr + x.dyn_off);
+          j.n_inter = h.key_frame ? 0 : n_mb;  // placeholders: the kernels read `dyn`
+          j.n_intra = n_mb;
+          any_modes = true;
+          any_wave = true;
+        }
       }
       std::memcpy(j.dq, h.dq, sizeof(j.dq));
       j.key_frame = h.key_frame;
@@ -507,7 +585,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
 
   if (any_tokens) {
     ScopedTimer t(e, 5);
-    CU_TRY(vp8r::LaunchTokens(sl.d_jobs, n, max_cols, e->st));
+    CU_TRY(vp8r::LaunchTokens(sl.d_jobs, n, max_cols, max_mbs, any_modes, e->st));
     e->acc.launches_other++;
   }
   if (any_inter) {
@@ -519,6 +597,10 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
     ScopedTimer t(e, 1);
     for (size_t L = 0; L < level_max.size(); ++L) {
       CU_TRY(vp8r::LaunchIntraFlat(sl.d_jobs, n, int(L), level_max[L], e->st));
+      e->acc.launches_intra++;
+    }
+    if (any_modes) {
+      CU_TRY(vp8r::LaunchIntraLevels(sl.d_jobs, n, e->st));
       e->acc.launches_intra++;
     }
     if (any_wave) {
@@ -626,10 +708,13 @@ VP8R_API int vp8r_read_batch_packed(vp8r_engine *e, int n, vp8r_stream *const *s
   const size_t bytes = size_t(n) * stride;
   if (bytes > e->pack_cap) {
     CU_TRY(cudaStreamSynchronize(e->st));
+    CU_TRY(cudaStreamSynchronize(e->st_copy));
+    e->copy_busy[0] = e->copy_busy[1] = false;
     if (e->d_pack) cudaFree(e->d_pack);
     e->d_pack = nullptr;
-    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_pack), bytes + 256));
-    e->pack_cap = bytes;
+    const size_t half = (bytes + 255) & ~size_t(255);
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_pack), 2 * half + 256));
+    e->pack_cap = half;
   }
   // job table: reuse the checksum scratch, growing it if needed
   if (n > e->cap_cjobs) {
@@ -647,25 +732,39 @@ VP8R_API int vp8r_read_batch_packed(vp8r_engine *e, int n, vp8r_stream *const *s
     CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_sums), sizeof(uint64_t) * cap));
     e->cap_cjobs = cap;
   }
-  // Two halves of the table alternate so that an in-flight asynchronous copy of the previous call
-  // is not overwritten on the host side.
+  // Two halves of the job table and of the staging buffer alternate: the pack kernel of this call
+  // runs on the engine's stream while the D2H copy of the previous call may still be in flight on
+  // the copy stream.
   e->pack_flip ^= 1;
-  DevFrameJob *hj = e->h_cjobs + size_t(e->pack_flip) * e->cap_cjobs;
-  DevFrameJob *dj = e->d_cjobs + size_t(e->pack_flip) * e->cap_cjobs;
+  const int half = e->pack_flip;
+  uint8_t *stage = e->d_pack + size_t(half) * e->pack_cap;
+  DevFrameJob *hj = e->h_cjobs + size_t(half) * e->cap_cjobs;
+  DevFrameJob *dj = e->d_cjobs + size_t(half) * e->cap_cjobs;
+  if (e->copy_busy[half]) {  // the copy that last read this half (two calls ago) must be done
+    CU_TRY(cudaEventSynchronize(e->copy_done[half]));  // host side: hj is about to be rewritten
+    e->copy_busy[half] = false;
+  }
   for (int i = 0; i < n; ++i) {
     DevFrameJob &j = hj[i];
     std::memset(&j, 0, sizeof(j));
     FillJobSurfaces(streams[i], streams[i]->ref[0], &j);
-    j.pack_dst = e->d_pack + size_t(i) * stride;
+    j.pack_dst = stage + size_t(i) * stride;
   }
   {
     ScopedTimer t(e, 4);
     CU_TRY(cudaMemcpyAsync(dj, hj, sizeof(DevFrameJob) * n, cudaMemcpyHostToDevice, e->st));
     CU_TRY(vp8r::LaunchPack(dj, n, e->st));
     e->acc.launches_other++;
-    CU_TRY(cudaMemcpyAsync(dst, e->d_pack, bytes, cudaMemcpyDeviceToHost, e->st));
   }
-  if (!async) CU_TRY(cudaStreamSynchronize(e->st));
+  CU_TRY(cudaEventRecord(e->pack_done[half], e->st));
+  CU_TRY(cudaStreamWaitEvent(e->st_copy, e->pack_done[half], 0));
+  CU_TRY(cudaMemcpyAsync(dst, stage, bytes, cudaMemcpyDeviceToHost, e->st_copy));
+  CU_TRY(cudaEventRecord(e->copy_done[half], e->st_copy));
+  e->copy_busy[half] = true;
+  if (!async) {
+    CU_TRY(cudaStreamSynchronize(e->st_copy));
+    e->copy_busy[half] = false;
+  }
   return VP8R_OK;
 }
 
@@ -752,6 +851,13 @@ VP8R_API int vp8r_engine_fence(vp8r_engine *e, uint64_t *ticket) {
   cudaEvent_t &ev = e->fence_ev[t & 15];
   if (!ev) CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CU_TRY(cudaEventRecord(ev, e->st));
+  // ... and everything queued on the copy stream (asynchronous packed read-backs)
+  e->fence_has_copy[t & 15] = e->copy_busy[0] || e->copy_busy[1];
+  if (e->fence_has_copy[t & 15]) {
+    cudaEvent_t &cev = e->fence_copy_ev[t & 15];
+    if (!cev) CU_TRY(cudaEventCreateWithFlags(&cev, cudaEventDisableTiming));
+    CU_TRY(cudaEventRecord(cev, e->st_copy));
+  }
   *ticket = t;
   return VP8R_OK;
 }
@@ -764,6 +870,7 @@ VP8R_API int vp8r_engine_wait(vp8r_engine *e, uint64_t ticket) {
   }
   if (e->fence_head - ticket > 16) return VP8R_OK;  // recycled: a later fence on the same stream was recorded over it
   CU_TRY(cudaEventSynchronize(e->fence_ev[ticket & 15]));
+  if (e->fence_has_copy[ticket & 15]) CU_TRY(cudaEventSynchronize(e->fence_copy_ev[ticket & 15]));
   return VP8R_OK;
 }
 

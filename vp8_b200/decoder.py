@@ -57,6 +57,11 @@ class Parser:
         decoded by the engine's token kernel (vp8r_frame_hdr.tokens_deferred)."""
         self._lib.vp8r_parser_set_defer_tokens(self.handle, 1 if on else 0)
 
+    def set_defer_modes(self, on=True):
+        """Frame headers only on the host; the per-macroblock syntax of the first partition and the
+        DCT partitions are decoded by the engine's parse kernel (vp8r_frame_hdr.modes_deferred)."""
+        self._lib.vp8r_parser_set_defer_modes(self.handle, 1 if on else 0)
+
     def close(self):
         if self.handle:
             self._lib.vp8r_parser_destroy(self.handle)
