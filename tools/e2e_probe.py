@@ -1,0 +1,38 @@
+#!/usr/bin/env python3
+"""Development probe: where the end-to-end time goes (parse mode x read-back on/off)."""
+import os, sys, time, tempfile, shutil
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench, vp8_b200
+from concurrent.futures import ThreadPoolExecutor
+
+S = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+tmp = tempfile.mkdtemp()
+paths = [os.path.join(tmp, f"s{k}.ivf") for k in range(S)]
+with ThreadPoolExecutor(max_workers=os.cpu_count()) as ex:
+    list(ex.map(lambda k: bench.synth_stream(7122 + k, paths[k]), range(S)))
+payloads = [vp8_b200.read_ivf(p)[1] for p in paths]
+shutil.rmtree(tmp, ignore_errors=True)
+stream = torch.cuda.Stream()
+eng = vp8_b200.Engine(0, cuda_stream=stream.cuda_stream)
+eng.set_timing(True)
+ring = [torch.empty((S, bench.FRAME_BYTES), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+packed = ((ring[0].data_ptr(), ring[1].data_ptr()), bench.FRAME_BYTES)
+MODES = sys.argv[2].split(",") if len(sys.argv) > 2 else ["host", "tokens", "device"]
+RB = [bool(int(x)) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [False, True]
+for mode in MODES:
+    for rb in RB:
+        dec = vp8_b200.BatchDecoder(eng, S, parse_threads=os.cpu_count(), pinned=True,
+                                    tokens_on_device=mode == "tokens", device_parse=mode == "device")
+        dec.decode(payloads, out_packed=packed if rb else None)
+        torch.cuda.synchronize()
+        eng.timers(reset=True)
+        t0 = time.perf_counter()
+        dec.reset()
+        dec.decode(payloads, out_packed=packed if rb else None)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tm = eng.timers(reset=True)
+        print(f"{mode:7s} readback={rb!s:5s} {S*30/dt:8.0f} fps  wall {dt*1e3:7.0f} ms  tokens {tm.ms_tokens:6.0f} recon {tm.ms_inter+tm.ms_intra+tm.ms_filter:6.0f} h2d {tm.ms_h2d:5.0f} pack {tm.ms_d2h:5.0f}", flush=True)
+        dec.close()
+eng.close()

@@ -15,6 +15,7 @@
 // All arithmetic is integer and bit-exact with the reference, including its int16 wrap-arounds.
 #include "recon_kernels.h"
 
+#include <algorithm>
 #include <cstring>
 
 namespace vp8r {
@@ -1161,6 +1162,41 @@ __global__ void __launch_bounds__(256) PackKernel(const DevFrameJob *__restrict_
       for (int k = 0; k < n; ++k) d[k] = (uint8_t)(v >> (8 * k));
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// host -> device staging by the SMs (zero-copy reads of pinned host memory)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) CopyKernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+constexpr int kGatherChunk = 16 * 1024;  // bytes per CTA
+__global__ void __launch_bounds__(256) GatherKernel(const DevFrameJob *__restrict__ jobs) {
+  const DevFrameJob &job = jobs[blockIdx.y];
+  const size_t bytes = job.h2d_bytes;
+  const size_t begin = (size_t)blockIdx.x * kGatherChunk;
+  if (begin >= bytes) return;
+  const size_t end = min(bytes, begin + (size_t)kGatherChunk);
+  const uint4 *src = reinterpret_cast<const uint4 *>(job.h2d_src);
+  uint4 *dst = reinterpret_cast<uint4 *>(job.h2d_dst);
+  // 4 loads in flight per thread: PCIe reads need depth, not width
+  for (size_t i = begin / 16 + threadIdx.x; i < (end + 15) / 16; i += 256) dst[i] = src[i];
+}
+
+cudaError_t LaunchCopy(void *dst, const void *src_pinned, size_t bytes, cudaStream_t st) {
+  const size_t n16 = (bytes + 15) / 16;
+  if (n16 == 0) return cudaSuccess;
+  const int grid = (int)std::min<size_t>((n16 + 255) / 256, 148 * 4);
+  CopyKernel<<<grid, 256, 0, st>>>(static_cast<uint4 *>(dst), static_cast<const uint4 *>(src_pinned), n16);
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchGather(const DevFrameJob *jobs, int n_frames, size_t max_bytes, cudaStream_t st) {
+  if (max_bytes == 0 || n_frames == 0) return cudaSuccess;
+  dim3 grid((unsigned)((max_bytes + kGatherChunk - 1) / kGatherChunk), n_frames);
+  GatherKernel<<<grid, 256, 0, st>>>(jobs);
+  return cudaGetLastError();
 }
 
 cudaError_t LaunchPack(const DevFrameJob *jobs, int n_frames, cudaStream_t st) {

@@ -53,6 +53,10 @@ struct DevFrameJob {
   // intra level table and `dyn`; the segment map persists per stream
   const uint8_t *mode_hdr;
   uint32_t split_base;
+  // staging by LaunchGather: h2d_bytes of the frame's blob at pinned host address h2d_src -> h2d_dst
+  uint32_t h2d_bytes;
+  const uint8_t *h2d_src;
+  uint8_t *h2d_dst;
   uint8_t *segment_map;
   uint32_t *level_table;
   DevFrameDyn *dyn;
@@ -86,6 +90,11 @@ cudaError_t LaunchIntraFlat(const DevFrameJob *jobs, int n_frames, int level, in
 // `sync`: device scratch of `sync_ints` ints (ticket + one progress word per (frame, band)).
 cudaError_t LaunchFilter(const DevFrameJob *jobs, int n_frames, int max_rows, int *sync, int sync_ints,
                          cudaStream_t st);
+// Host->device staging without the copy engines (which the packed read-back keeps busy): `src` is
+// pinned host memory read by the SMs over PCIe.  LaunchCopy moves one buffer (bytes % 16 == 0, both
+// 16-byte aligned); LaunchGather moves every job's blob (h2d_src -> h2d_dst, h2d_bytes).
+cudaError_t LaunchCopy(void *dst, const void *src_pinned, size_t bytes, cudaStream_t st);
+cudaError_t LaunchGather(const DevFrameJob *jobs, int n_frames, size_t max_bytes, cudaStream_t st);
 // Device-side crop + I420 pack of each job's current surface into job.pack_dst.
 cudaError_t LaunchPack(const DevFrameJob *jobs, int n_frames, cudaStream_t st);
 // Device-side checksum of the cropped I420 image of each job's current surface.

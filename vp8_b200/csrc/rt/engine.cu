@@ -85,6 +85,7 @@ struct Slot {
   uint8_t *d_arena = nullptr;
   size_t arena_cap = 0;
   cudaEvent_t done = nullptr;
+  cudaEvent_t parsed = nullptr;  // staging + parse kernel of this slot's batch finished (on st_parse)
   bool pending = false;
 };
 }  // namespace
@@ -103,6 +104,10 @@ struct vp8r_engine {
   uint8_t *d_pack = nullptr;
   size_t pack_cap = 0;  // bytes per half
   cudaStream_t st_copy = nullptr;
+  // parse stream: staging + K_tokens of time step t+1 run here while the reconstruction kernels of
+  // step t run on `st` (the parse kernel is a few hundred latency-bound threads; it leaves the SMs'
+  // issue slots to the reconstruction kernels)
+  cudaStream_t st_parse = nullptr;
   cudaEvent_t pack_done[2] = {}, copy_done[2] = {};
   bool copy_busy[2] = {false, false};
   cudaEvent_t fence_copy_ev[16] = {};
@@ -180,6 +185,7 @@ int ConfigureStream(vp8r_stream *s, const vp8r_frame_hdr &h) {
     s->height = h.height;
     return VP8R_OK;
   }
+  CU_TRY(cudaStreamSynchronize(s->eng->st_parse));
   CU_TRY(cudaStreamSynchronize(s->eng->st));
   FreeSurfaces(s);
   const int B = vp8r::kBorder;
@@ -211,6 +217,7 @@ int ConfigureStream(vp8r_stream *s, const vp8r_frame_hdr &h) {
     s->d_segmap = static_cast<uint8_t *>(p);
     CU_TRY(cudaMemsetAsync(p, 0, n_mb + 256, s->eng->st));
   }
+  CU_TRY(cudaStreamSynchronize(s->eng->st));  // the clears must land before the parse stream touches the new buffers
   s->mb_cols = h.mb_cols;
   s->mb_rows = h.mb_rows;
   s->width = h.width;
@@ -229,8 +236,8 @@ int GrowSlot(vp8r_engine *e, Slot &sl, int n_jobs, size_t arena_bytes) {
     if (sl.d_jobs) cudaFree(sl.d_jobs);
     sl.h_jobs = nullptr;
     sl.d_jobs = nullptr;
-    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_jobs), sizeof(DevFrameJob) * cap, cudaHostAllocDefault));
-    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&sl.d_jobs), sizeof(DevFrameJob) * cap));
+    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_jobs), sizeof(DevFrameJob) * cap + 16, cudaHostAllocDefault));
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&sl.d_jobs), sizeof(DevFrameJob) * cap + 16));
     sl.cap_jobs = cap;
   }
   if (arena_bytes > sl.arena_cap) {
@@ -261,15 +268,17 @@ struct ScopedTimer {
   vp8r_engine *e;
   EventPair p;
   bool on;
-  ScopedTimer(vp8r_engine *eng, int cls) : e(eng), on(eng->timing) {
+  cudaStream_t stream;
+  ScopedTimer(vp8r_engine *eng, int cls, cudaStream_t on_stream = nullptr)
+      : e(eng), on(eng->timing), stream(on_stream ? on_stream : eng->st) {
     if (on) {
       p = GetPair(e, cls);
-      cudaEventRecord(p.a, e->st);
+      cudaEventRecord(p.a, stream);
     }
   }
   ~ScopedTimer() {
     if (on) {
-      cudaEventRecord(p.b, e->st);
+      cudaEventRecord(p.b, stream);
       e->live.push_back(p);
     }
   }
@@ -348,8 +357,12 @@ VP8R_API int vp8r_engine_create(int device, void *cuda_stream, vp8r_engine **out
     }
     e->own_stream = true;
   }
-  for (auto &sl : e->slots) cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+  for (auto &sl : e->slots) {
+    cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&sl.parsed, cudaEventDisableTiming);
+  }
   cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&e->st_parse, cudaStreamNonBlocking);
   for (int k = 0; k < 2; ++k) {
     cudaEventCreateWithFlags(&e->pack_done[k], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->copy_done[k], cudaEventDisableTiming);
@@ -380,6 +393,10 @@ VP8R_API void vp8r_engine_destroy(vp8r_engine *e) {
     cudaStreamSynchronize(e->st_copy);
     cudaStreamDestroy(e->st_copy);
   }
+  if (e->st_parse) {
+    cudaStreamSynchronize(e->st_parse);
+    cudaStreamDestroy(e->st_parse);
+  }
   for (int k = 0; k < 2; ++k) {
     if (e->pack_done[k]) cudaEventDestroy(e->pack_done[k]);
     if (e->copy_done[k]) cudaEventDestroy(e->copy_done[k]);
@@ -391,6 +408,7 @@ VP8R_API void vp8r_engine_destroy(vp8r_engine *e) {
     if (sl.d_jobs) cudaFree(sl.d_jobs);
     if (sl.d_arena) cudaFree(sl.d_arena);
     if (sl.done) cudaEventDestroy(sl.done);
+    if (sl.parsed) cudaEventDestroy(sl.parsed);
   }
   if (e->h_cjobs) cudaFreeHost(e->h_cjobs);
   if (e->d_cjobs) cudaFree(e->d_cjobs);
@@ -412,6 +430,7 @@ VP8R_API void vp8r_engine_destroy(vp8r_engine *e) {
 
 VP8R_API int vp8r_engine_sync(vp8r_engine *e) {
   if (!e) return VP8R_ERR_INVALID_ARG;
+  CU_TRY(cudaStreamSynchronize(e->st_parse));
   CU_TRY(cudaStreamSynchronize(e->st));
   CU_TRY(cudaStreamSynchronize(e->st_copy));
   e->copy_busy[0] = e->copy_busy[1] = false;
@@ -504,10 +523,15 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
   int max_mbs = 0, max_rows = 0, max_cols = 0;
   bool any_inter = false, any_intra = false, any_wave = false, any_tokens = false, any_modes = false;
   std::vector<int> level_max;  // per dependency level: most intra MBs of that level in any frame
-  size_t at = 0;
+  size_t at = 0, gather_max = 0;
   std::vector<int> cur_idx(n);
+  // Staging and the parse kernel go to the parse stream when any frame has deferred tokens, so that
+  // they overlap the reconstruction kernels of the previous time step on `st`.
+  bool deferred = false;
+  for (int i = 0; i < n; ++i) deferred |= frames[i]->hdr.tokens_deferred != 0;
+  cudaStream_t front = deferred ? e->st_parse : e->st;
   {
-    ScopedTimer t(e, 3);
+    ScopedTimer t(e, 3, front);
     for (int i = 0; i < n; ++i) {
       vp8r_stream *s = streams[i];
       vp8r_frame *f = frames[i];
@@ -525,7 +549,14 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
         dev_blob = static_cast<const uint8_t *>(f->d_blob);
       } else {
         uint8_t *dst = sl.d_arena + at;
-        CU_TRY(cudaMemcpyAsync(dst, f->blob, f->used_bytes(), cudaMemcpyHostToDevice, e->st));
+        if (f->pinned) {  // staged by the gather kernel below (SM reads of pinned memory, no copy engine)
+          j.h2d_src = f->blob;
+          j.h2d_dst = dst;
+          j.h2d_bytes = uint32_t(f->used_bytes());
+          gather_max = std::max(gather_max, f->used_bytes());
+        } else {
+          CU_TRY(cudaMemcpyAsync(dst, f->blob, f->used_bytes(), cudaMemcpyHostToDevice, front));
+        }
         dev_blob = dst;
         at += FrameDevExtra(f).total;
       }
@@ -580,13 +611,20 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
       e->acc.coef_blocks += h.n_coef_blocks;
       e->acc.alg_bytes += uint64_t(n_mb) * 384 * (h.key_frame ? 1 : 2) + uint64_t(h.n_coef_blocks) * 32;
     }
-    CU_TRY(cudaMemcpyAsync(sl.d_jobs, sl.h_jobs, sizeof(DevFrameJob) * n, cudaMemcpyHostToDevice, e->st));
+    static_assert(sizeof(DevFrameJob) % 8 == 0, "job table is copied in 16-byte units");
+    CU_TRY(vp8r::LaunchCopy(sl.d_jobs, sl.h_jobs, sizeof(DevFrameJob) * n, front));
+    CU_TRY(vp8r::LaunchGather(sl.d_jobs, n, gather_max, front));
+    e->acc.launches_other += 2;
   }
 
   if (any_tokens) {
-    ScopedTimer t(e, 5);
-    CU_TRY(vp8r::LaunchTokens(sl.d_jobs, n, max_cols, max_mbs, any_modes, e->st));
+    ScopedTimer t(e, 5, front);
+    CU_TRY(vp8r::LaunchTokens(sl.d_jobs, n, max_cols, max_mbs, any_modes, front));
     e->acc.launches_other++;
+  }
+  if (front != e->st) {
+    CU_TRY(cudaEventRecord(sl.parsed, front));
+    CU_TRY(cudaStreamWaitEvent(e->st, sl.parsed, 0));
   }
   if (any_inter) {
     ScopedTimer t(e, 0);
@@ -726,8 +764,8 @@ VP8R_API int vp8r_read_batch_packed(vp8r_engine *e, int n, vp8r_stream *const *s
     e->h_cjobs = e->d_cjobs = nullptr;
     e->h_sums = e->d_sums = nullptr;
     int cap = std::max(n, 64);
-    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_cjobs), sizeof(DevFrameJob) * cap * 2, cudaHostAllocDefault));
-    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_cjobs), sizeof(DevFrameJob) * cap * 2));
+    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_cjobs), sizeof(DevFrameJob) * cap * 2 + 16, cudaHostAllocDefault));
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_cjobs), sizeof(DevFrameJob) * cap * 2 + 16));
     CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_sums), sizeof(uint64_t) * cap, cudaHostAllocDefault));
     CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_sums), sizeof(uint64_t) * cap));
     e->cap_cjobs = cap;
@@ -752,7 +790,7 @@ VP8R_API int vp8r_read_batch_packed(vp8r_engine *e, int n, vp8r_stream *const *s
   }
   {
     ScopedTimer t(e, 4);
-    CU_TRY(cudaMemcpyAsync(dj, hj, sizeof(DevFrameJob) * n, cudaMemcpyHostToDevice, e->st));
+    CU_TRY(vp8r::LaunchCopy(dj, hj, sizeof(DevFrameJob) * n, e->st));
     CU_TRY(vp8r::LaunchPack(dj, n, e->st));
     e->acc.launches_other++;
   }
@@ -789,8 +827,8 @@ VP8R_API int vp8r_checksum_batch(vp8r_engine *e, int n, vp8r_stream *const *stre
     e->h_cjobs = e->d_cjobs = nullptr;
     e->h_sums = e->d_sums = nullptr;
     int cap = std::max(n, 64);
-    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_cjobs), sizeof(DevFrameJob) * cap * 2, cudaHostAllocDefault));
-    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_cjobs), sizeof(DevFrameJob) * cap * 2));
+    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_cjobs), sizeof(DevFrameJob) * cap * 2 + 16, cudaHostAllocDefault));
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_cjobs), sizeof(DevFrameJob) * cap * 2 + 16));
     CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_sums), sizeof(uint64_t) * cap, cudaHostAllocDefault));
     CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_sums), sizeof(uint64_t) * cap));
     e->cap_cjobs = cap;
