@@ -73,7 +73,8 @@ cudaError_t InitKernelTables();
 
 // K_tokens: device-side token decode of every job with tok_hdr != nullptr (see token_kernel.cu).
 // `modes`: some job also has mode_hdr (one more working thread per frame, more shared memory).
-cudaError_t LaunchTokens(const DevFrameJob *jobs, int n_frames, int max_cols, int max_mbs, bool modes, cudaStream_t st);
+cudaError_t LaunchTokens(const DevFrameJob *jobs, int n_frames, int max_cols, int max_mbs, int max_parts, bool modes,
+                         cudaStream_t st);
 cudaError_t InitParseTables();
 // Level-scheduled intra prediction of frames whose level table was built on the device: one CTA per
 // frame walks the dependency levels with a block barrier in between.

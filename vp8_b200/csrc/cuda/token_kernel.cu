@@ -47,7 +47,8 @@ struct ModeTables {
       tree_split[6], tree_submv[6], tree_smallmv[14];
   unsigned char prob_ymode_key[4], prob_uvmode_key[3], prob_bmode_inter[9], prob_split[3], prob_submv[5][3],
       prob_mvref[6][4];
-  unsigned char split_count[4], split_map[4][16], split_head[4][16];
+  unsigned char split_count[4], split_head[4][16];
+  unsigned short split_mask[4][16];  // [layout][partition]: the sub-blocks it covers
   unsigned char kf_bmode[900];
 };
 __constant__ ModeTables c_mode_tables;
@@ -69,11 +70,12 @@ const ModeTables kModeTablesInit = {
     {{147, 136, 18}, {106, 145, 1}, {179, 121, 1}, {223, 1, 34}, {208, 1, 1}},
     {{7, 1, 1, 143}, {14, 18, 14, 107}, {135, 64, 57, 68}, {60, 56, 128, 65}, {159, 134, 128, 34}, {234, 188, 128, 28}},
     {2, 2, 4, 16},
-    {{0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1},
-     {0, 0, 1, 1, 0, 0, 1, 1, 0, 0, 1, 1, 0, 0, 1, 1},
-     {0, 0, 1, 1, 0, 0, 1, 1, 2, 2, 3, 3, 2, 2, 3, 3},
-     {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}},
     {{0, 8}, {0, 2}, {0, 2, 8, 10}, {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}},
+    {{0x00ff, 0xff00},
+     {0x3333, 0xcccc},
+     {0x0033, 0x00cc, 0x3300, 0xcc00},
+     {0x0001, 0x0002, 0x0004, 0x0008, 0x0010, 0x0020, 0x0040, 0x0080, 0x0100, 0x0200, 0x0400, 0x0800, 0x1000, 0x2000,
+      0x4000, 0x8000}},
     {0}};
 
 __constant__ unsigned char c_band[17] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0};
@@ -292,6 +294,7 @@ __device__ void ModeThread(const DevFrameJob &job, const vp8r_token_hdr *th, uns
   unsigned sign_bias = 0;
   for (int i = 0; i < 4; ++i) sign_bias |= (unsigned)(mhp->sign_bias[i] != 0) << i;
   // small per-frame probability sets live in shared memory behind the token probabilities' CTA copy
+  __shared__ int sub[16];           // sub-block motion vectors of the current SPLIT macroblock
   __shared__ unsigned char fp[64];  // [0..3] ymode, [4..6] uvmode, [8..10] segment tree, [16..53] mv
   for (int i = 0; i < 4; ++i) fp[i] = mhp->ymode_probs[i];
   for (int i = 0; i < 3; ++i) fp[4 + i] = mhp->uvmode_probs[i], fp[8 + i] = mhp->segment_tree_probs[i];
@@ -320,9 +323,13 @@ __device__ void ModeThread(const DevFrameJob &job, const vp8r_token_hdr *th, uns
     unsigned left_level = 0, aboveleft_level = 0;
     const int to_top = -(r * 16) * 8, to_bottom = ((rows - 1 - r) * 16) * 8;
 
+    const bool read_map = !update_map && !key;
+    unsigned seg_next = read_map ? segmap[r * cols] : 0u;  // fetched one macroblock ahead
     for (int c = 0; c < cols; ++c) {
       const int idx = r * cols + c;
       const uint2 above_ctx = r > 0 ? ctx_abv[c] : make_uint2(0, 0);
+      const unsigned seg_cur = seg_next;
+      if (read_map && c + 1 < cols) seg_next = segmap[idx + 1];
       // --- pre-header (src/bitstream_parser.cc:320-352) ---
       int seg;
       if (update_map) {
@@ -332,7 +339,7 @@ __device__ void ModeThread(const DevFrameJob &job, const vp8r_token_hdr *th, uns
         seg = 0;  // a key frame rebuilds the parser context: the persistent map starts from zero
         segmap[idx] = 0;
       } else {
-        seg = segmap[idx];
+        seg = (int)seg_cur;
       }
       const int skip = no_skip ? bd.Bit(prob_skip) : 0;
       const int is_inter = key ? 0 : bd.Bit(prob_intra);
@@ -340,7 +347,6 @@ __device__ void ModeThread(const DevFrameJob &job, const vp8r_token_hdr *th, uns
       unsigned flags = 0, aux0 = 0, aux1 = 0;
       int mbmv = 0, ref = 0, inter_mode = 0;
       bool split = false, bpred = false;
-      int sub[16];
       if (is_inter) {
         ref = bd.Bit(prob_last) ? 2 + bd.Bit(prob_gf) : 1;
         // ---- neighbour search (src/inter_predict.cc:8-81) ----
@@ -430,8 +436,10 @@ __device__ void ModeThread(const DevFrameJob &job, const vp8r_token_hdr *th, uns
               else if (sm == SUB_ABOVE) v = amv;
               else if (sm == SUB_ZERO) v = 0;
               else v = read_new();
+              const unsigned members = T.split_mask[layout][part];
+#pragma unroll
               for (int b = 0; b < 16; ++b)
-                if (T.split_map[layout][b] == part) sub[b] = v;
+                if ((members >> b) & 1u) sub[b] = v;
             }
             mbmv = sub[15];
             break;
@@ -543,8 +551,10 @@ __device__ void ModeThread(const DevFrameJob &job, const vp8r_token_hdr *th, uns
           for (int k = 0; k < 4; ++k) above_sub[c * 4 + k] = mbmv, left_sub[k] = mbmv;
         }
       }
-      __threadfence_block();
-      *done = idx + 1;
+      if ((idx & 3) == 3 || idx + 1 == n_mb) {  // the token threads follow a few macroblocks behind
+        __threadfence_block();
+        *done = idx + 1;
+      }
     }
   }
 
@@ -576,7 +586,11 @@ __device__ void ModeThread(const DevFrameJob &job, const vp8r_token_hdr *th, uns
   if (bd.BytesConsumed() > (int)mhp->first_size && job.status) atomicOr(job.status, 2);
 }
 
-__global__ void __launch_bounds__((kTokenWarps + 1) * 32) TokenKernel(const DevFrameJob *__restrict__ jobs) {
+// Block = (most DCT partitions of any frame in the batch + 1) warps; the mode thread is the last warp.
+// Only one lane per warp works, but registers are allocated for all 32: the register cap (and the
+// trimmed block) keep a batch's footprint small enough to share the SMs with the reconstruction
+// kernels of the previous time step.
+__global__ void __launch_bounds__((kTokenWarps + 1) * 32, 4) TokenKernel(const DevFrameJob *__restrict__ jobs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const DevFrameJob &job = jobs[blockIdx.x];
   if (!job.tok_hdr) return;
@@ -603,7 +617,7 @@ __global__ void __launch_bounds__((kTokenWarps + 1) * 32) TokenKernel(const DevF
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane != 0) return;
-  if (warp == kTokenWarps) {
+  if (warp == (int)(blockDim.x >> 5) - 1) {  // last warp: macroblock headers
     if (modes) ModeThread(job, th, smem_raw, sh);
     return;
   }
@@ -733,7 +747,8 @@ cudaError_t InitParseTables() {
 
 size_t ParseKernelSmem(int max_cols, int max_mbs, bool modes) { return MakeLayout(max_cols, max_mbs, modes).total + 16; }
 
-cudaError_t LaunchTokens(const DevFrameJob *jobs, int n_frames, int max_cols, int max_mbs, bool modes, cudaStream_t st) {
+cudaError_t LaunchTokens(const DevFrameJob *jobs, int n_frames, int max_cols, int max_mbs, int max_parts, bool modes,
+                         cudaStream_t st) {
   const size_t smem = ParseKernelSmem(max_cols, max_mbs, modes);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
@@ -741,7 +756,8 @@ cudaError_t LaunchTokens(const DevFrameJob *jobs, int n_frames, int max_cols, in
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  TokenKernel<<<n_frames, (kTokenWarps + 1) * 32, smem, st>>>(jobs);
+  max_parts = max_parts < 1 ? 1 : (max_parts > kTokenWarps ? kTokenWarps : max_parts);
+  TokenKernel<<<n_frames, (max_parts + 1) * 32, smem, st>>>(jobs);
   return cudaGetLastError();
 }
 

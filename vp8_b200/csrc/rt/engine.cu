@@ -520,7 +520,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
   if (rc) return rc;
 
   // Pass 2: jobs + host->device staging.
-  int max_mbs = 0, max_rows = 0, max_cols = 0;
+  int max_mbs = 0, max_rows = 0, max_cols = 0, max_parts = 1;
   bool any_inter = false, any_intra = false, any_wave = false, any_tokens = false, any_modes = false;
   std::vector<int> level_max;  // per dependency level: most intra MBs of that level in any frame
   size_t at = 0, gather_max = 0;
@@ -584,6 +584,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
         j.status = e->d_status;
         any_tokens = true;
         max_cols = std::max(max_cols, int(h.mb_cols));
+        max_parts = std::max(max_parts, int(reinterpret_cast<const vp8r_token_hdr *>(f->payload() + size_t(h.tokens_at) * 16)->n_parts));
         if (h.modes_deferred) {
           j.mode_hdr = reinterpret_cast<const uint8_t *>(j.payload + size_t(h.modes_at) * 16);
           j.mbs = reinterpret_cast<const vp8r_mb_info *>(wr + x.mb_off);
@@ -619,7 +620,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
 
   if (any_tokens) {
     ScopedTimer t(e, 5, front);
-    CU_TRY(vp8r::LaunchTokens(sl.d_jobs, n, max_cols, max_mbs, any_modes, front));
+    CU_TRY(vp8r::LaunchTokens(sl.d_jobs, n, max_cols, max_mbs, max_parts, any_modes, front));
     e->acc.launches_other++;
   }
   if (front != e->st) {
