@@ -799,6 +799,9 @@ int FrameParser::Parse(const uint8_t *data, size_t size, vp8r_frame *out) {
         }
   }
 
+  const bool fits_device = size_t(mb_cols_) * mb_rows_ <= kMaxDeferMbs;
+  defer_modes_ = want_defer_modes_ && fits_device;
+  defer_tokens_ = (want_defer_tokens_ || want_defer_modes_) && fits_device;
   out->n_mb = defer_modes_ ? 0 : size_t(mb_cols_) * mb_rows_;  // deferred modes: no host MB records
   out->hdr.n_coef_blocks = out->hdr.n_payload_blocks = 0;
   if (!out->Reserve(out->mb_bytes() + 64 * 1024, 0)) return Fail(VP8R_ERR_NOMEM, "out of host memory");

@@ -35,10 +35,10 @@ class FrameParser {
   const std::string &error() const { return error_; }
   // Deferred tokens: parse the first partition only and attach the DCT partitions to the frame for
   // the device-side token decoder (vp8r_frame_hdr.tokens_deferred).  Survives Reset().
-  void set_defer_tokens(bool on) { defer_tokens_ = on; }
+  void set_defer_tokens(bool on) { want_defer_tokens_ = on; }
   // Deferred modes: parse the frame header only; the per-macroblock syntax is decoded on the device
   // too (vp8r_frame_hdr.modes_deferred).  Implies deferred tokens.
-  void set_defer_modes(bool on) { defer_modes_ = on; }
+  void set_defer_modes(bool on) { want_defer_modes_ = on; }
 
  private:
   struct Mv {
@@ -81,6 +81,9 @@ class FrameParser {
   bool BuildIntraLevels(vp8r_frame *out);
   bool AttachTokenPartitions(vp8r_frame *out);
   static constexpr unsigned kMaxFlatIntraLevels = 48;
+  // Largest frame (macroblocks) whose tokens / modes are deferred: the device parse kernel keeps two
+  // bytes per macroblock in shared memory.  Larger frames are parsed on the host as usual.
+  static constexpr size_t kMaxDeferMbs = 65536;
 
   // ---- state that persists between frames (ParserContext, src/bitstream_parser.h:124-182) ----
   bool have_key_ = false;
@@ -98,8 +101,8 @@ class FrameParser {
   const uint8_t *dct_data_[8] = {};  // start / size of each DCT partition inside the compressed frame
   size_t dct_size_[8] = {};
   int n_dct_parts_ = 1;
-  bool defer_tokens_ = false;
-  bool defer_modes_ = false;
+  bool defer_tokens_ = false, defer_modes_ = false;          // what the caller asked for
+  bool want_defer_tokens_ = false, want_defer_modes_ = false;
   const uint8_t *first_data_ = nullptr;  // first partition inside the compressed frame
   size_t first_size_ = 0;
   bool key_frame_ = false;
