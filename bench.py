@@ -159,10 +159,14 @@ def main():
     ap.add_argument("--streams", type=int, default=256, help="independent 1080p streams per GPU")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-parse", default="device", choices=["host", "tokens", "device"],
+    ap.add_argument("--e2e-parse", default="mix", choices=["host", "tokens", "device", "mix"],
                     help="end-to-end pass: where the bitstream is parsed. host: everything on host threads; tokens: "
                          "first partition on the host, DCT token partitions on the GPU; device: frame headers on the "
-                         "host, all per-macroblock syntax on the GPU (default)")
+                         "host, all per-macroblock syntax on the GPU; mix (default): tokens on the GPU, macroblock "
+                         "headers on the GPU for --device-share of the streams and on host threads for the rest")
+    ap.add_argument("--device-share", type=float, default=None,
+                    help="mix: share of the streams whose macroblock headers are decoded on the GPU "
+                         "(default 1 - 0.5/n_gpus: the host cores are shared by all ranks)")
     ap.add_argument("--serial-setup", action="store_true", help="generate the streams one at a time (for runs under ncu)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -266,9 +270,12 @@ def main():
         f.close()
     dec.close()
     e2e_dec = vp8_b200.BatchDecoder(eng, S, parse_threads=max(1, min(S, (os.cpu_count() or 1) // max(1, world))), pinned=True,
-                                   tokens_on_device=args.e2e_parse == "tokens", device_parse=args.e2e_parse == "device")
-    ring_t = [torch.empty((S, FRAME_BYTES), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-    packed = ((ring_t[0].data_ptr(), ring_t[1].data_ptr()), FRAME_BYTES)  # device-side crop+pack, one D2H per step
+                                   tokens_on_device=args.e2e_parse == "tokens",
+                                   device_parse={"device": True, "mix": device_share}.get(args.e2e_parse, False), depth=DEPTH)
+    device_share = args.device_share if args.device_share is not None else 1.0 - 0.5 / world
+    DEPTH = 4  # time steps in flight between host parse and the arrival of the frames in host memory
+    ring_t = [torch.empty((S, FRAME_BYTES), dtype=torch.uint8, pin_memory=True) for _ in range(DEPTH)]
+    packed = (tuple(r.data_ptr() for r in ring_t), FRAME_BYTES)  # device-side crop+pack, one D2H per step
     e2e_dec.decode(payloads, out_packed=packed)  # warm-up (allocations, pinned buffers growth)
     barrier()
     t0 = time.perf_counter()
@@ -317,7 +324,8 @@ def main():
                     "mp_per_s": e2e_value * W * H / 1e6, "steps": args.e2e_steps,
                     "kernel_ms_per_step": (tm2.ms_inter + tm2.ms_intra + tm2.ms_filter) / max(1, args.e2e_steps + 1),
                     "token_kernel_ms_per_step": tm2.ms_tokens / max(1, args.e2e_steps + 1),
-                    "parse": args.e2e_parse},
+                    "parse": args.e2e_parse, "device_header_share": device_share if args.e2e_parse == "mix" else None,
+                    "steps_in_flight": DEPTH},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

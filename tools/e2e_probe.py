@@ -16,14 +16,16 @@ shutil.rmtree(tmp, ignore_errors=True)
 stream = torch.cuda.Stream()
 eng = vp8_b200.Engine(0, cuda_stream=stream.cuda_stream)
 eng.set_timing(True)
-ring = [torch.empty((S, bench.FRAME_BYTES), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-packed = ((ring[0].data_ptr(), ring[1].data_ptr()), bench.FRAME_BYTES)
+DEPTH = int(sys.argv[4]) if len(sys.argv) > 4 else 4
+ring = [torch.empty((S, bench.FRAME_BYTES), dtype=torch.uint8, pin_memory=True) for _ in range(DEPTH)]
+packed = (tuple(r.data_ptr() for r in ring), bench.FRAME_BYTES)
 MODES = sys.argv[2].split(",") if len(sys.argv) > 2 else ["host", "tokens", "device"]
 RB = [bool(int(x)) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [False, True]
 for mode in MODES:
     for rb in RB:
         dec = vp8_b200.BatchDecoder(eng, S, parse_threads=os.cpu_count(), pinned=True,
-                                    tokens_on_device=mode == "tokens", device_parse=mode == "device")
+                                    tokens_on_device=mode == "tokens", depth=DEPTH,
+                                    device_parse=(True if mode == "device" else float(mode[3:]) if mode.startswith("mix") else False))
         dec.decode(payloads, out_packed=packed if rb else None)
         torch.cuda.synchronize()
         eng.timers(reset=True)

@@ -14,7 +14,10 @@ from .decoder import ParsedFrame, Parser
 
 
 class BatchDecoder:
-    def __init__(self, engine, n_streams, parse_threads=None, pinned=True, tokens_on_device=False, device_parse=False):
+    def __init__(self, engine, n_streams, parse_threads=None, pinned=True, tokens_on_device=False, device_parse=False,
+                 depth=2):
+        """depth: time steps in flight (parsed-frame slots; out_ring / out_packed passed to decode()
+        must hold as many buffers).  The engine supports up to 4."""
         self.engine = engine
         self._lib = engine._lib
         self.n = n_streams
@@ -26,10 +29,19 @@ class BatchDecoder:
             for p in self.parsers:
                 p.set_defer_tokens(True)
         if device_parse:      # host: frame headers only; device: all per-macroblock syntax
-            for p in self.parsers:
-                p.set_defer_modes(True)
+            # device_parse may be a fraction: that share of the streams has its macroblock headers
+            # decoded on the device, the rest on host threads (both feed the same batched launches),
+            # which balances the host cores against the GPU's header threads
+            share = 1.0 if device_parse is True else float(device_parse)
+            n_dev = int(round(share * n_streams))
+            for k, p in enumerate(self.parsers):
+                if k < n_dev:
+                    p.set_defer_modes(True)
+                else:
+                    p.set_defer_tokens(True)
         self.streams = [engine.open_stream() for _ in range(n_streams)]
-        self.slots = [[ParsedFrame(pinned=pinned) for _ in range(n_streams)] for _ in range(2)]
+        self.depth = max(2, min(4, depth))
+        self.slots = [[ParsedFrame(pinned=pinned) for _ in range(n_streams)] for _ in range(self.depth)]
 
     def reset(self):
         for p in self.parsers:
@@ -67,11 +79,11 @@ class BatchDecoder:
         check(self._lib.vp8r_engine_wait(self.engine.handle, ticket))
 
     def decode(self, payloads, out_ring=None, on_step=None, out_packed=None):
-        """payloads[s] = list of compressed frames of stream s.  out_ring: optional list of two lists
+        """payloads[s] = list of compressed frames of stream s.  out_ring: optional list of `depth` lists
         of (ptr, capacity) pinned host buffers, one per stream, that receive the frames of a time step
-        (ring of two steps).  out_packed: optional ((ptr0, ptr1), stride): two pinned host buffers; the
-        frames of a time step are cropped and packed on the device and arrive with one copy, frame k
-        of the step's live streams at ptr + k*stride.  on_step(t, live, frames) is called after step t
+        (ring of `depth` steps).  out_packed: optional ((ptr0, ptr1, ...), stride): `depth` pinned host
+        buffers; the frames of a time step are cropped and packed on the device and arrive with one copy,
+        frame k of the step's live streams at ptr + k*stride.  on_step(t, live, frames) is called after step t
         has been submitted.
         Returns (frames decoded, frames shown, h2d bytes, d2h bytes)."""
         steps = max(len(p) for p in payloads)
@@ -88,21 +100,22 @@ class BatchDecoder:
                 h2d += (0 if d.hdr.modes_deferred else d.hdr.mb_cols * d.hdr.mb_rows * 32) + d.hdr.n_payload_blocks * 32
                 shown += d.hdr.show_frame
             if out_ring is not None:
-                ring = out_ring[t & 1]
+                ring = out_ring[t % self.depth]
                 self.engine.read_batch(streams, [ring[i][0] for i in live], [ring[i][1] for i in live], async_=True)
                 d2h += sum(s.frame_bytes() for s in streams)
             if out_packed is not None:
                 (ptrs, stride) = out_packed
-                self.engine.read_batch_packed(streams, ptrs[t & 1], stride, async_=True)
+                self.engine.read_batch_packed(streams, ptrs[t % self.depth], stride, async_=True)
                 d2h += len(streams) * stride
             tickets[t] = self.fence()
             if on_step:
                 on_step(t, live, frames)
             if t + 1 < steps:
-                if t - 1 in tickets:
-                    self.wait(tickets.pop(t - 1))  # slot (t+1)&1 and ring (t+1)&1 are free again
+                old = t + 1 - self.depth
+                if old in tickets:
+                    self.wait(tickets.pop(old))  # slot and ring entry (t+1) % depth are free again
                 live = [i for i in range(self.n) if len(payloads[i]) > t + 1]
-                frames = self.parse_step((t + 1) & 1, [p[t + 1] if len(p) > t + 1 else b"" for p in payloads], live)
+                frames = self.parse_step((t + 1) % self.depth, [p[t + 1] if len(p) > t + 1 else b"" for p in payloads], live)
         self.engine.sync()
         return decoded, shown, h2d, d2h
 

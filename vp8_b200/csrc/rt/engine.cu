@@ -94,7 +94,9 @@ struct vp8r_engine {
   int device = 0;
   cudaStream_t st = nullptr;
   bool own_stream = false;
-  Slot slots[2];
+  static constexpr int kSlots = 4;     // batches in flight between the host and the last kernel
+  static constexpr int kPackBufs = 4;  // packed read-backs in flight
+  Slot slots[kSlots];
   int cur_slot = 0;
   // ticket + per-(frame, band) progress words of the wavefront kernels
   int *d_sync = nullptr;
@@ -108,8 +110,8 @@ struct vp8r_engine {
   // step t run on `st` (the parse kernel is a few hundred latency-bound threads; it leaves the SMs'
   // issue slots to the reconstruction kernels)
   cudaStream_t st_parse = nullptr;
-  cudaEvent_t pack_done[2] = {}, copy_done[2] = {};
-  bool copy_busy[2] = {false, false};
+  cudaEvent_t pack_done[4] = {}, copy_done[4] = {};
+  bool copy_busy[4] = {false, false, false, false};
   cudaEvent_t fence_copy_ev[16] = {};
   bool fence_has_copy[16] = {};
   // checksum scratch
@@ -363,7 +365,7 @@ VP8R_API int vp8r_engine_create(int device, void *cuda_stream, vp8r_engine **out
   }
   cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&e->st_parse, cudaStreamNonBlocking);
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < vp8r_engine::kPackBufs; ++k) {
     cudaEventCreateWithFlags(&e->pack_done[k], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->copy_done[k], cudaEventDisableTiming);
   }
@@ -397,7 +399,7 @@ VP8R_API void vp8r_engine_destroy(vp8r_engine *e) {
     cudaStreamSynchronize(e->st_parse);
     cudaStreamDestroy(e->st_parse);
   }
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < vp8r_engine::kPackBufs; ++k) {
     if (e->pack_done[k]) cudaEventDestroy(e->pack_done[k]);
     if (e->copy_done[k]) cudaEventDestroy(e->copy_done[k]);
   }
@@ -433,7 +435,7 @@ VP8R_API int vp8r_engine_sync(vp8r_engine *e) {
   CU_TRY(cudaStreamSynchronize(e->st_parse));
   CU_TRY(cudaStreamSynchronize(e->st));
   CU_TRY(cudaStreamSynchronize(e->st_copy));
-  e->copy_busy[0] = e->copy_busy[1] = false;
+  for (bool &b : e->copy_busy) b = false;
   for (auto &sl : e->slots) sl.pending = false;
   if (e->h_status && *static_cast<volatile int *>(e->h_status) != 0) {
     *e->h_status = 0;
@@ -511,7 +513,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
     if (!(f->d_blob && f->d_device == e->device)) arena += FrameDevExtra(f).total;
   }
   Slot &sl = e->slots[e->cur_slot];
-  e->cur_slot ^= 1;
+  e->cur_slot = (e->cur_slot + 1) % vp8r_engine::kSlots;
   if (sl.pending) {
     CU_TRY(cudaEventSynchronize(sl.done));
     sl.pending = false;
@@ -748,11 +750,11 @@ VP8R_API int vp8r_read_batch_packed(vp8r_engine *e, int n, vp8r_stream *const *s
   if (bytes > e->pack_cap) {
     CU_TRY(cudaStreamSynchronize(e->st));
     CU_TRY(cudaStreamSynchronize(e->st_copy));
-    e->copy_busy[0] = e->copy_busy[1] = false;
+    for (bool &b : e->copy_busy) b = false;
     if (e->d_pack) cudaFree(e->d_pack);
     e->d_pack = nullptr;
     const size_t half = (bytes + 255) & ~size_t(255);
-    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_pack), 2 * half + 256));
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_pack), vp8r_engine::kPackBufs * half + 256));
     e->pack_cap = half;
   }
   // job table: reuse the checksum scratch, growing it if needed
@@ -765,21 +767,21 @@ VP8R_API int vp8r_read_batch_packed(vp8r_engine *e, int n, vp8r_stream *const *s
     e->h_cjobs = e->d_cjobs = nullptr;
     e->h_sums = e->d_sums = nullptr;
     int cap = std::max(n, 64);
-    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_cjobs), sizeof(DevFrameJob) * cap * 2 + 16, cudaHostAllocDefault));
-    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_cjobs), sizeof(DevFrameJob) * cap * 2 + 16));
+    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_cjobs), sizeof(DevFrameJob) * cap * vp8r_engine::kPackBufs + 16, cudaHostAllocDefault));
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_cjobs), sizeof(DevFrameJob) * cap * vp8r_engine::kPackBufs + 16));
     CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_sums), sizeof(uint64_t) * cap, cudaHostAllocDefault));
     CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_sums), sizeof(uint64_t) * cap));
     e->cap_cjobs = cap;
   }
-  // Two halves of the job table and of the staging buffer alternate: the pack kernel of this call
+  // kPackBufs parts of the job table and of the staging buffer rotate: the pack kernel of this call
   // runs on the engine's stream while the D2H copy of the previous call may still be in flight on
   // the copy stream.
-  e->pack_flip ^= 1;
+  e->pack_flip = (e->pack_flip + 1) % vp8r_engine::kPackBufs;
   const int half = e->pack_flip;
   uint8_t *stage = e->d_pack + size_t(half) * e->pack_cap;
   DevFrameJob *hj = e->h_cjobs + size_t(half) * e->cap_cjobs;
   DevFrameJob *dj = e->d_cjobs + size_t(half) * e->cap_cjobs;
-  if (e->copy_busy[half]) {  // the copy that last read this half (two calls ago) must be done
+  if (e->copy_busy[half]) {  // the copy that last read this part (kPackBufs calls ago) must be done
     CU_TRY(cudaEventSynchronize(e->copy_done[half]));  // host side: hj is about to be rewritten
     e->copy_busy[half] = false;
   }
@@ -828,8 +830,8 @@ VP8R_API int vp8r_checksum_batch(vp8r_engine *e, int n, vp8r_stream *const *stre
     e->h_cjobs = e->d_cjobs = nullptr;
     e->h_sums = e->d_sums = nullptr;
     int cap = std::max(n, 64);
-    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_cjobs), sizeof(DevFrameJob) * cap * 2 + 16, cudaHostAllocDefault));
-    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_cjobs), sizeof(DevFrameJob) * cap * 2 + 16));
+    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_cjobs), sizeof(DevFrameJob) * cap * vp8r_engine::kPackBufs + 16, cudaHostAllocDefault));
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_cjobs), sizeof(DevFrameJob) * cap * vp8r_engine::kPackBufs + 16));
     CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_sums), sizeof(uint64_t) * cap, cudaHostAllocDefault));
     CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_sums), sizeof(uint64_t) * cap));
     e->cap_cjobs = cap;
@@ -891,7 +893,8 @@ VP8R_API int vp8r_engine_fence(vp8r_engine *e, uint64_t *ticket) {
   if (!ev) CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CU_TRY(cudaEventRecord(ev, e->st));
   // ... and everything queued on the copy stream (asynchronous packed read-backs)
-  e->fence_has_copy[t & 15] = e->copy_busy[0] || e->copy_busy[1];
+  e->fence_has_copy[t & 15] = false;
+  for (bool b : e->copy_busy) e->fence_has_copy[t & 15] |= b;
   if (e->fence_has_copy[t & 15]) {
     cudaEvent_t &cev = e->fence_copy_ev[t & 15];
     if (!cev) CU_TRY(cudaEventCreateWithFlags(&cev, cudaEventDisableTiming));
