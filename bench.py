@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=256, help="independent 1080p streams per GPU")
+    ap.add_argument("--streams", type=int, default=512, help="independent 1080p streams per GPU")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-parse", default="mix", choices=["host", "tokens", "device", "mix"],
@@ -269,11 +269,11 @@ def main():
     for f in (f for fr in resident for f in fr):
         f.close()
     dec.close()
+    device_share = args.device_share if args.device_share is not None else 1.0 - 0.5 / world
+    DEPTH = 4  # time steps in flight between host parse and the arrival of the frames in host memory
     e2e_dec = vp8_b200.BatchDecoder(eng, S, parse_threads=max(1, min(S, (os.cpu_count() or 1) // max(1, world))), pinned=True,
                                    tokens_on_device=args.e2e_parse == "tokens",
                                    device_parse={"device": True, "mix": device_share}.get(args.e2e_parse, False), depth=DEPTH)
-    device_share = args.device_share if args.device_share is not None else 1.0 - 0.5 / world
-    DEPTH = 4  # time steps in flight between host parse and the arrival of the frames in host memory
     ring_t = [torch.empty((S, FRAME_BYTES), dtype=torch.uint8, pin_memory=True) for _ in range(DEPTH)]
     packed = (tuple(r.data_ptr() for r in ring_t), FRAME_BYTES)  # device-side crop+pack, one D2H per step
     e2e_dec.decode(payloads, out_packed=packed)  # warm-up (allocations, pinned buffers growth)
@@ -300,7 +300,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_DECODE):
         cores = min(os.cpu_count() or 1, 64)
         with tempfile.TemporaryDirectory() as td:
-            n_fr = 10
+            n_fr = 30
             paths = cpu_sample(cores, n_fr, td)
             dt = run_reference_cpu(paths, cores)
         cpu = {"value": cores * n_fr / dt, "unit": "frames/s", "cores": cores, "kind": "reference",

@@ -395,3 +395,84 @@ def test_device_tokens_batched_and_truncated(engine):
     engine.sync()  # the flag is cleared once reported
     fr.close()
     st.close()
+
+
+def test_device_parse_truncated_first_partition(engine):
+    """Deferred modes: a first partition that ends early is reported by vp8r_engine_sync
+    (VP8R_ERR_TRUNCATED), like the host parser does for the same bytes."""
+    import vp8_b200
+    from vp8_b200._capi import Vp8rError
+    ivf = helpers.synth_stream("--width 320 --height 192 --frames 2 --seed 9 --log2-parts 0")
+    key = vp8_b200.read_ivf(ivf)[1][0]
+    first_size = (key[0] | key[1] << 8 | key[2] << 16) >> 5
+    # keep the start code and headers, shorten the declared first partition: the macroblock headers
+    # then run past its end while the DCT partition (the bytes behind it) is still present
+    cut = first_size // 2
+    tag = (key[0] | key[1] << 8 | key[2] << 16) & 0x1f | (cut << 5)
+    bad = bytes([tag & 0xff, (tag >> 8) & 0xff, (tag >> 16) & 0xff]) + key[3:10 + cut] + key[10 + first_size:]
+    host = vp8_b200.Parser()
+    with pytest.raises(Vp8rError) as e0:
+        host.parse(bad)
+    assert e0.value.code == 4
+    ps = vp8_b200.Parser()
+    ps.set_defer_modes(True)
+    st = engine.open_stream()
+    fr = ps.parse(bad, pinned=True)
+    engine.reconstruct_batch([st], [fr])
+    with pytest.raises(Vp8rError) as e1:
+        engine.sync()
+    assert e1.value.code == 4
+    engine.sync()
+    fr.close()
+    st.close()
+
+
+def test_device_parse_survives_corrupted_streams(engine):
+    """Bit flips / garbage in the partitions (the frame header kept valid): the device-side parse must
+    neither hang nor fault; whatever it decodes equals what the host parser + oracle make of the same
+    bytes whenever the host parser accepts them."""
+    import random
+    import vp8_b200
+    from vp8_b200._capi import Vp8rError
+    rng = random.Random(4242)
+    base = helpers.synth_stream("--width 96 --height 80 --frames 5 --seed 5 --log2-parts 2 --pct-split 30 --pct-intra 20")
+    _, payloads = vp8_b200.read_ivf(base)
+    compared = flagged = 0
+    for trial in range(40):
+        host, dev, orc = vp8_b200.Parser(), vp8_b200.Parser(), helpers.Oracle()
+        dev.set_defer_modes(True)
+        st = engine.open_stream()
+        try:
+            for k, pl in enumerate(payloads):
+                data = bytearray(pl)
+                hdr = 10 if k == 0 else 3
+                lo = hdr + 60  # keep the frame header (probability updates etc.) intact
+                for _ in range(rng.randint(1, 6)):
+                    data[rng.randrange(lo, len(data))] ^= 1 << rng.randrange(8)
+                data = bytes(data)
+                host_ok = True
+                try:
+                    want = orc.decode(host.parse(data))
+                except Vp8rError:
+                    host_ok = False
+                try:
+                    fr = dev.parse(data, pinned=True)
+                except Vp8rError:
+                    break  # header-level rejection: same code path as the host parser
+                engine.reconstruct_batch([st], [fr])
+                try:
+                    engine.sync()
+                    dev_ok = True
+                except Vp8rError as e:
+                    assert e.code == 4
+                    dev_ok = False
+                    flagged += 1
+                fr.close()
+                if not (host_ok and dev_ok):
+                    break  # the stream is dead for both from here on
+                assert st.read_frame() == want, f"trial {trial} frame {k}"
+                compared += 1
+        finally:
+            st.close()
+            orc.close()
+    assert compared > 40
