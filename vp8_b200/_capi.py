@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libvp8r.so")
+LIB_PATH = os.environ.get("VP8R_LIB") or os.path.join(_HERE, "_lib", "libvp8r.so")  # VP8R_LIB: development builds
 
 
 class MbInfo(C.Structure):

@@ -26,6 +26,8 @@ namespace vp8r {
 // Sub-pixel filter taps packed as signed bytes: [bilinear][frac][0] = taps 0..3, [..][1] = taps 4,5.
 // frac 0 (identity, tap 128) is special-cased and never looked up.
 __constant__ int c_taps[2][8][2];
+// The same taps as plain integers, for the packed 16x2 vertical pass: [bilinear][frac][tap].
+__constant__ int c_taps6[2][8][6];
 // B_PRED gather table: [mode][pixel] -> i0 | i1<<4 | i2<<8 | kind<<12 over the 13-entry edge
 // array E = {L3,L2,L1,L0,P,A0..A7}.  kind 0: (E[i0]+2E[i1]+E[i2]+2)>>2, 1: (E[i0]+E[i2]+1)>>1,
 // 2: DC, 3: TM = clamp(E[i0]+E[i1]-E[i2]).
@@ -95,6 +97,14 @@ cudaError_t InitKernelTables() {
     taps[1][f][1] = 0;
   }
   cudaError_t err = cudaMemcpyToSymbol(c_taps, taps, sizeof(taps));
+  if (err != cudaSuccess) return err;
+  int taps6[2][8][6];
+  for (int f = 0; f < 8; ++f)
+    for (int k = 0; k < 6; ++k) {
+      taps6[0][f][k] = six[f][k];
+      taps6[1][f][k] = k == 2 ? 128 - 16 * f : (k == 3 ? 16 * f : 0);
+    }
+  err = cudaMemcpyToSymbol(c_taps6, taps6, sizeof(taps6));
   if (err != cudaSuccess) return err;
   err = InitParseTables();
   if (err != cudaSuccess) return err;
@@ -246,10 +256,203 @@ __device__ __forceinline__ void Transpose4x4(unsigned r0, unsigned r1, unsigned 
   c3 = __byte_perm(t2, t3, 0x7632);
 }
 
+// Saturating pack of four ints to bytes (o0 lowest): two I2IP.  cvt.pack: d = c<<16 | sat(a)<<8 | sat(b).
+__device__ __forceinline__ unsigned PackSat4(int o0, int o1, int o2, int o3) {
+  unsigned t, d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(o3), "r"(o2), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(o1), "r"(o0), "r"(t));
+  return d;
+}
+
+// Filter4 with the rounding shift and the clamp+pack done by I2IP.
+__device__ __forceinline__ unsigned Filter4P(unsigned lo, unsigned mid, unsigned hi, int t03, int t45) {
+  int s[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    unsigned a = j ? __funnelshift_r(lo, mid, 8 * j) : lo;
+    unsigned b = j ? __funnelshift_r(mid, hi, 8 * j) : mid;
+    s[j] = dp4a_us(b, t45, dp4a_us(a, t03, 64)) >> 7;
+  }
+  return PackSat4(s[0], s[1], s[2], s[3]);
+}
+
+// Vertical 6-tap on packed pixels: e[k] / o[k] hold pixels (0,2) / (1,3) of row k in 16-bit lanes.
+// acc = sum t[k]*row[k] per lane, in one 32-bit multiply-add per two pixels.  Lane sums lie in
+// [-8160, 40800]; the bias 8192 + 64 keeps both lanes non-negative (no borrow into the upper lane) and,
+// being 64*128 + rounding, comes out of the >>7 as +64, removed by the saturating add.
+__device__ __forceinline__ unsigned Vert6(const unsigned *e, const unsigned *o, const int *t) {
+  const unsigned bias = (8192u + 64u) * 0x00010001u;
+  unsigned ae = bias, ao = bias;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    ae += (unsigned)t[k] * e[k];
+    ao += (unsigned)t[k] * o[k];
+  }
+  ae = (ae >> 7) & 0x01ff01ffu;
+  ao = (ao >> 7) & 0x01ff01ffu;
+  ae = __vmins2(__viaddmax_s16x2(ae, 0xffc0ffc0u, 0u), 0x00ff00ffu);  // clamp(x - 64, 0, 255) per lane
+  ao = __vmins2(__viaddmax_s16x2(ao, 0xffc0ffc0u, 0u), 0x00ff00ffu);
+  return ae | (ao << 8);
+}
+
+// clamp255(int16(pred + res)) on 4 packed pixels; r01 / r23 hold the four int16 residuals.
+__device__ __forceinline__ unsigned AddResidual4(unsigned pred, unsigned r01, unsigned r23) {
+  const unsigned pe = __byte_perm(pred, 0, 0x4240), po = __byte_perm(pred, 0, 0x4341);
+  const unsigned re = __byte_perm(r01, r23, 0x5410), ro = __byte_perm(r01, r23, 0x7632);
+  const unsigned se = __vmins2(__vmaxs2(__vadd2(pe, re), 0u), 0x00ff00ffu);  // 16-bit wrap-around add, as the reference
+  const unsigned so = __vmins2(__vmaxs2(__vadd2(po, ro), 0u), 0x00ff00ffu);
+  return se | (so << 8);
+}
+
+// Per-warp scratch of the macroblock-level motion compensation.
+struct __align__(16) InterScratch {
+  unsigned hl[21 * 4];     // luma after the horizontal pass: 21 rows x 16 pixels
+  unsigned hc[2][13 * 2];  // U, V after the horizontal pass: 13 rows x 8 pixels
+  short res[24][16];       // residual of the 24 blocks
+  short y2[16];
+};
+
+// Motion compensation of a non-SPLIT inter macroblock by one warp (src/inter_predict.cc:246-333): the
+// 16x16 luma block and the two 8x8 chroma blocks each have ONE vector, so the reference window is
+// fetched and filtered once per macroblock (21x21 / 13x13) instead of once per 4x4 block (9x9 each):
+// horizontal pass (dp4a on byte-shifted words) into shared memory, vertical pass on packed 16-bit
+// lanes, residual add, store.
+__device__ __forceinline__ void InterMacroblockWhole(const DevFrameJob &job, const vp8r_mb_info &mb, int mb_r, int mb_c,
+                                                     int lane, InterScratch &s, bool has_res) {
+  const int ref_id = (mb.flags >> VP8R_MB_REF_SHIFT) & 3;
+  const int bil = job.version != 0;
+  const int mvr = mb.mv[0], mvc = mb.mv[1];
+  // chroma vector: 4 x the luma vector, rounded away from zero, / 8 (src/inter_predict.cc:116-144)
+  const int sr = s16(4 * mvr), sc = s16(4 * mvc);
+  int cmr = (sr >= 0 ? (sr + 4) : (sr - 4)) / 8, cmc = (sc >= 0 ? (sc + 4) : (sc - 4)) / 8;
+  if (job.version == 3) {
+    cmr &= ~7;
+    cmc &= ~7;
+  }
+  const int fr = mvr & 7, fc = mvc & 7, cfr = cmr & 7, cfc = cmc & 7;
+
+  // ---- horizontal pass: all window words of this lane are requested first (15 loads in flight), then
+  // filtered.  Luma task = (window row, output word), three rounds; chroma: one round per plane. ----
+  {
+    const int pitch = job.pitch_y, cpitch = job.pitch_c;
+    int wy = mb_r * 16 + (mvr >> 3) - 2, wx = mb_c * 16 + (mvc >> 3) - 2;
+    wy = min(max(wy, -kBorder), job.mb_rows * 16 + kBorder - 21);
+    wx = min(max(wx, -kBorder), job.mb_cols * 16 + kBorder - 21);
+    const uint8_t *wp = job.ref[ref_id].y + (ptrdiff_t)wy * pitch + wx;
+    const unsigned shift = ((unsigned)(size_t)wp & 3u) * 8;
+    const int w = lane & 3, row0 = lane >> 2;
+    unsigned lw[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int row = min(row0 + 8 * k, 20);  // rows past the window re-read its last row (not used)
+      const unsigned *p = reinterpret_cast<const unsigned *>(wp - ((size_t)wp & 3)) + row * (pitch >> 2) + w;
+      lw[k][0] = p[0]; lw[k][1] = p[1]; lw[k][2] = p[2];
+    }
+    int cwy = mb_r * 8 + (cmr >> 3) - 2, cwx = mb_c * 8 + (cmc >> 3) - 2;
+    cwy = min(max(cwy, -kBorder), job.mb_rows * 8 + kBorder - 13);
+    cwx = min(max(cwx, -kBorder), job.mb_cols * 8 + kBorder - 13);
+    const int crow = min(lane >> 1, 12), cw_ = lane & 1;
+    const ptrdiff_t coff = (ptrdiff_t)cwy * cpitch + cwx;
+    const uint8_t *up = job.ref[ref_id].u + coff, *vp = job.ref[ref_id].v + coff;
+    const unsigned cshift = ((unsigned)(size_t)up & 3u) * 8;  // U and V planes are congruent mod 4 (256-byte aligned bases)
+    unsigned cw[2][3];
+    {
+      const unsigned *pu = reinterpret_cast<const unsigned *>(up - ((size_t)up & 3)) + crow * (cpitch >> 2) + cw_;
+      const unsigned *pv = reinterpret_cast<const unsigned *>(vp - ((size_t)vp & 3)) + crow * (cpitch >> 2) + cw_;
+      cw[0][0] = pu[0]; cw[0][1] = pu[1]; cw[0][2] = pu[2];
+      cw[1][0] = pv[0]; cw[1][1] = pv[1]; cw[1][2] = pv[2];
+    }
+    {
+      const int r_lo = fr ? 0 : 2, r_hi = fr ? 21 : 18;
+      const int t03 = c_taps[bil][fc][0], t45 = c_taps[bil][fc][1];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int row = row0 + 8 * k;
+        if (row >= r_lo && row < r_hi) {
+          const unsigned lo = __funnelshift_r(lw[k][0], lw[k][1], shift), mid = __funnelshift_r(lw[k][1], lw[k][2], shift),
+                         hi = lw[k][2] >> shift;
+          s.hl[row * 4 + w] = fc ? Filter4P(lo, mid, hi, t03, t45) : __funnelshift_r(lo, mid, 16);
+        }
+      }
+    }
+    {
+      const int r_lo = cfr ? 0 : 2, r_hi = cfr ? 13 : 10;
+      const int t03 = c_taps[bil][cfc][0], t45 = c_taps[bil][cfc][1];
+      const int row = lane >> 1;
+      if (row >= r_lo && row < r_hi) {
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+          const unsigned lo = __funnelshift_r(cw[pl][0], cw[pl][1], cshift), mid = __funnelshift_r(cw[pl][1], cw[pl][2], cshift),
+                         hi = cw[pl][2] >> cshift;
+          s.hc[pl][row * 2 + cw_] = cfc ? Filter4P(lo, mid, hi, t03, t45) : __funnelshift_r(lo, mid, 16);
+        }
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- vertical pass + residual + store, luma: lane = (output word w, row pair yg) ----
+  {
+    const int w = lane & 3, y0 = (lane >> 2) * 2;
+    unsigned out0, out1;
+    if (fr) {
+      unsigned e[7], o[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const unsigned r = s.hl[(y0 + k) * 4 + w];
+        e[k] = __byte_perm(r, 0, 0x4240);
+        o[k] = __byte_perm(r, 0, 0x4341);
+      }
+      const int *t = c_taps6[bil][fr];
+      out0 = Vert6(e, o, t);
+      out1 = Vert6(e + 1, o + 1, t);
+    } else {
+      out0 = s.hl[(y0 + 2) * 4 + w];
+      out1 = s.hl[(y0 + 3) * 4 + w];
+    }
+    if (has_res) {
+      const uint2 *rp = reinterpret_cast<const uint2 *>(&s.res[(y0 >> 2) * 4 + w][(y0 & 3) * 4]);
+      const uint2 ra = rp[0], rb = rp[1];
+      out0 = AddResidual4(out0, ra.x, ra.y);
+      out1 = AddResidual4(out1, rb.x, rb.y);
+    }
+    uint8_t *d = job.cur.y + (ptrdiff_t)(mb_r * 16 + y0) * job.pitch_y + mb_c * 16 + 4 * w;
+    *reinterpret_cast<unsigned *>(d) = out0;
+    *reinterpret_cast<unsigned *>(d + job.pitch_y) = out1;
+  }
+  // ---- chroma: lane = (plane, row y, output word w) ----
+  {
+    const int pl = lane >> 4, y = (lane >> 1) & 7, w = lane & 1;
+    const unsigned *h = s.hc[pl];
+    unsigned out;
+    if (cfr) {
+      unsigned e[6], o[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const unsigned r = h[(y + k) * 2 + w];
+        e[k] = __byte_perm(r, 0, 0x4240);
+        o[k] = __byte_perm(r, 0, 0x4341);
+      }
+      out = Vert6(e, o, c_taps6[bil][cfr]);
+    } else {
+      out = h[(y + 2) * 2 + w];
+    }
+    if (has_res) {
+      const uint2 ra = *reinterpret_cast<const uint2 *>(&s.res[16 + pl * 4 + (y >> 2) * 2 + w][(y & 3) * 4]);
+      out = AddResidual4(out, ra.x, ra.y);
+    }
+    uint8_t *d = (pl ? job.cur.v : job.cur.u) + (ptrdiff_t)(mb_r * 8 + y) * job.pitch_c + mb_c * 8 + 4 * w;
+    *reinterpret_cast<unsigned *>(d) = out;
+  }
+}
+
 constexpr int kInterWarps = 4;
 
-__global__ void __launch_bounds__(kInterWarps * 32) InterKernel(const DevFrameJob *__restrict__ jobs) {
-  __shared__ short s_y2[kInterWarps][16];
+#ifndef VP8R_INTER_MINBLOCKS
+#define VP8R_INTER_MINBLOCKS 12  // 40 registers: measured best (8: 64 regs -8 %, 14: 32 regs with spills -10 %)
+#endif
+__global__ void __launch_bounds__(kInterWarps * 32, VP8R_INTER_MINBLOCKS) InterKernel(const DevFrameJob *__restrict__ jobs) {
+  __shared__ InterScratch s_scratch[kInterWarps];
   const DevFrameJob &job = jobs[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mb_index = blockIdx.x * kInterWarps + warp;
@@ -265,11 +468,30 @@ __global__ void __launch_bounds__(kInterWarps * 32) InterKernel(const DevFrameJo
   if (!(mb.flags & VP8R_MB_IS_INTER)) return;
 
   int res[16];
-  const bool has_res = WarpResidual(job, mb, lane, s_y2[warp], res);
-  if (lane >= 24) return;
-
+  InterScratch &scratch = s_scratch[warp];
+  const bool has_res = WarpResidual(job, mb, lane, scratch.y2, res);
   const int mb_r = mb_index / job.mb_cols, mb_c = mb_index - mb_r * job.mb_cols;
   const bool split = ((mb.flags >> VP8R_MB_MODE_SHIFT) & 7) == 4;
+  if (!split) {  // one vector for the whole macroblock: window fetched and filtered once
+    const bool mb_has_res = mb.coef_mask != 0;
+    if (mb_has_res && lane < 24) {
+      uint4 *dst = reinterpret_cast<uint4 *>(scratch.res[lane]);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        unsigned v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int a = has_res ? res[8 * q + 2 * i] : 0, b = has_res ? res[8 * q + 2 * i + 1] : 0;
+          v[i] = ((unsigned)a & 0xffffu) | ((unsigned)b << 16);
+        }
+        dst[q] = make_uint4(v[0], v[1], v[2], v[3]);
+      }
+    }
+    InterMacroblockWhole(job, mb, mb_r, mb_c, lane, scratch, mb_has_res);
+    return;
+  }
+  if (lane >= 24) return;
+
   const int ref_id = (mb.flags >> VP8R_MB_REF_SHIFT) & 3;
   const int *split_mv = reinterpret_cast<const int *>(job.payload + (size_t)mb.aux[0] * 16);
 
