@@ -184,7 +184,18 @@ def main():
         raise SystemExit("bench.py needs a B200: the reconstruction path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner to stdout when the communicator is created: keep stdout for
+        # the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     S = args.streams
     stream = torch.cuda.Stream()
     eng = vp8_b200.Engine(local_rank, cuda_stream=stream.cuda_stream)
@@ -208,8 +219,8 @@ def main():
     for t in range(FRAMES):
         frames = dec.parse_into([vp8_b200.ParsedFrame(pinned=False) for _ in range(S)], [p[t] for p in payloads], everyone)
         for f in frames:
-            eng.upload(f)
             shown_per_pass += f.desc().hdr.show_frame
+            eng.upload(f, release_host=True)  # the replay only needs the device copy
         resident.append(frames)
 
     def device_pass():
@@ -270,7 +281,9 @@ def main():
         f.close()
     dec.close()
     device_share = args.device_share if args.device_share is not None else 1.0 - 0.5 / world
-    DEPTH = 4  # time steps in flight between host parse and the arrival of the frames in host memory
+    # time steps in flight between host parse and the arrival of the frames in host memory (each holds
+    # S x 3.1 MB of pinned output; one step less when several ranks share the host's memory)
+    DEPTH = 4 if world == 1 else 3
     e2e_dec = vp8_b200.BatchDecoder(eng, S, parse_threads=max(1, min(S, (os.cpu_count() or 1) // max(1, world))), pinned=True,
                                    tokens_on_device=args.e2e_parse == "tokens",
                                    device_parse={"device": True, "mix": device_share}.get(args.e2e_parse, False), depth=DEPTH)

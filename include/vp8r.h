@@ -240,6 +240,10 @@ VP8R_API void vp8r_stream_close(vp8r_stream *s);
  * start with inputs resident on the device (kernel-only measurements, replays). */
 VP8R_API int vp8r_frame_upload(vp8r_engine *e, vp8r_frame *f);
 
+/* Frees the host arrays of an uploaded frame (the header stays readable; vp8r_frame_get_desc then
+ * fails).  For replays of many resident frames: a 1080p frame holds ~0.9 MB of host memory. */
+VP8R_API int vp8r_frame_release_host(vp8r_frame *f);
+
 /* DecodeFrame + RefreshRefFrames for n frames of n distinct streams, asynchronously on the
  * engine's CUDA stream.  frames[i] not uploaded are staged host->device inside the call. */
 VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *streams,

@@ -64,6 +64,7 @@ SIGNATURES = {
     "vp8r_stream_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "vp8r_stream_close": (None, [C.c_void_p]),
     "vp8r_frame_upload": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vp8r_frame_release_host": (C.c_int, [C.c_void_p]),
     "vp8r_reconstruct_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "vp8r_stream_frame_bytes": (C.c_size_t, [C.c_void_p]),
     "vp8r_stream_dims": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

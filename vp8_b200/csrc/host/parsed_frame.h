@@ -9,6 +9,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <vector>
 
 #include "vp8r.h"
 
@@ -29,6 +30,10 @@ struct vp8r_frame {
   void *d_blob = nullptr;
   size_t d_bytes = 0;
   int d_device = -1;
+  // what the engine needs on the host once the arrays live on the device (vp8r_frame_release_host):
+  // the number of intra macroblocks per dependency level and the number of DCT partitions
+  std::vector<uint32_t> level_counts;
+  uint32_t n_token_parts = 0;
 
   size_t mb_bytes() const { return n_mb * sizeof(vp8r_mb_info); }
   size_t used_bytes() const { return mb_bytes() + size_t(hdr.n_payload_blocks) * 32; }

@@ -484,6 +484,26 @@ VP8R_API int vp8r_frame_upload(vp8r_engine *e, vp8r_frame *f) {
   f->d_blob = p;
   f->d_bytes = bytes;
   f->d_device = e->device;
+  // host-side facts the batched submission needs, so that the host arrays may be released
+  f->level_counts.clear();
+  if (f->hdr.n_intra_levels) {
+    const uint32_t *tab = reinterpret_cast<const uint32_t *>(f->payload() + size_t(f->hdr.intra_levels_at) * 16);
+    for (uint32_t L = 0; L < f->hdr.n_intra_levels; ++L) f->level_counts.push_back(tab[L + 1] - tab[L]);
+  }
+  f->n_token_parts = f->hdr.tokens_deferred
+                         ? reinterpret_cast<const vp8r_token_hdr *>(f->payload() + size_t(f->hdr.tokens_at) * 16)->n_parts
+                         : 0;
+  return VP8R_OK;
+}
+
+VP8R_API int vp8r_frame_release_host(vp8r_frame *f) {
+  if (!f || !f->d_blob) {
+    SetError("vp8r_frame_release_host: the frame has no device copy");
+    return VP8R_ERR_STATE;
+  }
+  if (f->blob) vp8r::HostFree(f->blob, f->pinned);
+  f->blob = nullptr;
+  f->blob_cap = 0;
   return VP8R_OK;
 }
 
@@ -498,7 +518,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
   for (int i = 0; i < n; ++i) {
     vp8r_stream *s = streams[i];
     vp8r_frame *f = frames[i];
-    if (!s || !f || s->eng != e || !f->blob) {
+    if (!s || !f || s->eng != e || !(f->blob || (f->d_blob && f->d_device == e->device))) {
       SetError("null stream/frame or stream of another engine");
       return VP8R_ERR_INVALID_ARG;
     }
@@ -570,9 +590,14 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
       j.n_intra_levels = int(h.n_intra_levels);
       if (h.n_intra_levels) {
         j.intra_levels = reinterpret_cast<const uint32_t *>(j.payload + size_t(h.intra_levels_at) * 16);
-        const uint32_t *tab = reinterpret_cast<const uint32_t *>(f->payload() + size_t(h.intra_levels_at) * 16);
         if (level_max.size() < h.n_intra_levels) level_max.resize(h.n_intra_levels, 0);
-        for (uint32_t L = 0; L < h.n_intra_levels; ++L) level_max[L] = std::max(level_max[L], int(tab[L + 1] - tab[L]));
+        if (f->blob) {
+          const uint32_t *tab = reinterpret_cast<const uint32_t *>(f->payload() + size_t(h.intra_levels_at) * 16);
+          for (uint32_t L = 0; L < h.n_intra_levels; ++L) level_max[L] = std::max(level_max[L], int(tab[L + 1] - tab[L]));
+        } else {  // host arrays released after upload
+          for (uint32_t L = 0; L < h.n_intra_levels && L < f->level_counts.size(); ++L)
+            level_max[L] = std::max(level_max[L], int(f->level_counts[L]));
+        }
       } else if (j.n_intra > 0) {
         any_wave = true;
       }
@@ -586,7 +611,8 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
         j.status = e->d_status;
         any_tokens = true;
         max_cols = std::max(max_cols, int(h.mb_cols));
-        max_parts = std::max(max_parts, int(reinterpret_cast<const vp8r_token_hdr *>(f->payload() + size_t(h.tokens_at) * 16)->n_parts));
+        max_parts = std::max(max_parts, f->blob ? int(reinterpret_cast<const vp8r_token_hdr *>(f->payload() + size_t(h.tokens_at) * 16)->n_parts)
+                                                : int(f->n_token_parts));
         if (h.modes_deferred) {
           j.mode_hdr = reinterpret_cast<const uint8_t *>(j.payload + size_t(h.modes_at) * 16);
           j.mbs = reinterpret_cast<const vp8r_mb_info *>(wr + x.mb_off);

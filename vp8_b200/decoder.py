@@ -91,8 +91,11 @@ class Engine:
         fa = (C.c_void_p * n)(*[f.handle for f in frames])
         check(self._lib.vp8r_reconstruct_batch(self.handle, n, sa, fa))
 
-    def upload(self, frame):
+    def upload(self, frame, release_host=False):
+        """Copies the frame's arrays to HBM; release_host frees the host copy afterwards."""
         check(self._lib.vp8r_frame_upload(self.handle, frame.handle))
+        if release_host:
+            check(self._lib.vp8r_frame_release_host(frame.handle))
 
     def checksum_batch(self, streams):
         n = len(streams)
