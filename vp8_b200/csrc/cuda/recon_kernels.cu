@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(kFlatWarps * 32) IntraFlatKernel(const DevFram
   __shared__ __align__(16) unsigned short lut[160];
   __shared__ IntraScratch scratch[kFlatWarps];
   const DevFrameJob &job = jobs[blockIdx.y];
-  if (job.dyn || level >= job.n_intra_levels) return;  // device-built tables: IntraLevelsKernel
+  if (job.dyn || job.levels_in_one_launch || level >= job.n_intra_levels) return;  // handled by IntraLevelsKernel
   const unsigned first = __ldg(job.intra_levels + level), end = __ldg(job.intra_levels + level + 1);
   for (int i = threadIdx.x; i < 160; i += blockDim.x) lut[i] = c_bpred_lut[i];
   __syncthreads();
@@ -870,13 +870,13 @@ __global__ void __launch_bounds__(kLevelWarps * 32) IntraLevelsKernel(const DevF
   __shared__ __align__(16) unsigned short lut[160];
   __shared__ IntraScratch scratch[kLevelWarps];
   const DevFrameJob &job = jobs[blockIdx.x];
-  if (!job.dyn) return;
-  const int n_levels = job.dyn->n_intra_levels;
+  if (!job.dyn && !job.levels_in_one_launch) return;
+  const int n_levels = JobIntraLevels(job);
   if (n_levels == 0) return;
   for (int i = threadIdx.x; i < 160; i += blockDim.x) lut[i] = c_bpred_lut[i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t *tab = job.level_table;
+  const uint32_t *tab = JobLevelTable(job);
   const uint32_t *order = tab + n_levels + 1;
   for (int level = 0; level < n_levels; ++level) {
     const unsigned first = tab[level], end = tab[level + 1];
@@ -1113,7 +1113,9 @@ __global__ void __launch_bounds__(kFiltWarps * 32, kFiltCtasPerSm) FilterKernel(
     const vp8r_mb_info *mbrow = mbs + (size_t)r * cols;
     // software pipeline: words and flags of macroblock c+1 are loaded while c is being filtered
     unsigned nxt[4] = {0, 0, 0, 0};
-    unsigned nflags = __ldg(&mbrow[0].flags);
+    // flags of 32 macroblocks at a time, one per lane, handed out by shuffle (a per-macroblock
+    // prefetch register was spilled and made the warp wait for the load right away)
+    unsigned flags32 = lane < cols ? __ldg(&mbrow[lane].flags) : 0u;
     if (lane_on) {
       if (luma) {
         const uint4 t = *reinterpret_cast<const uint4 *>(rowp);
@@ -1130,9 +1132,9 @@ __global__ void __launch_bounds__(kFiltWarps * 32, kFiltCtasPerSm) FilterKernel(
 
     for (int c = 0; c < cols; ++c) {
       unsigned cur[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
-      const unsigned flags = nflags;
+      if (c && (c & 31) == 0) flags32 = c + lane < cols ? __ldg(&mbrow[c + lane].flags) : 0u;
+      const unsigned flags = __shfl_sync(0xffffffffu, flags32, c & 31);
       if (c + 1 < cols) {
-        nflags = __ldg(&mbrow[c + 1].flags);
         if (lane_on) {
           const uint8_t *np = rowp + (c + 1) * n;
           if (luma) {

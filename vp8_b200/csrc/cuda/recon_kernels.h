@@ -37,7 +37,8 @@ struct DevFrameJob {
   const uint32_t *intra_levels;     // n_intra_levels+1 offsets, then MB indices sorted by level
   int16_t dq[4][6];
   uint8_t key_frame, version, filter_type, lf_level, sharpness;
-  uint8_t pad[3];
+  uint8_t levels_in_one_launch;  // host-built level table walked by IntraLevelsKernel instead of one launch per level
+  uint8_t pad[2];
   // output side (crop / checksum)
   int width, height;
   unsigned long long *checksum;  // optional: receives the I420 checksum

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -124,6 +125,9 @@ struct vp8r_engine {
   uint64_t fence_head = 0;
   // device-visible error word written by K_tokens (mapped pinned host memory)
   int *h_status = nullptr, *d_status = nullptr;
+  // intra scheduling of host-parsed inter frames: one launch per dependency level (default) or one
+  // level-walking launch (VP8R_INTRA_ONE_LAUNCH=1)
+  bool intra_one_launch = false;
   // timing
   bool timing = false;
   std::vector<EventPair> live;
@@ -349,6 +353,7 @@ VP8R_API int vp8r_engine_create(int device, void *cuda_stream, vp8r_engine **out
   vp8r_engine *e = new (std::nothrow) vp8r_engine();
   if (!e) return VP8R_ERR_NOMEM;
   e->device = device;
+  if (const char *v = std::getenv("VP8R_INTRA_ONE_LAUNCH")) e->intra_one_launch = v[0] == '1';
   if (cuda_stream) {
     e->st = static_cast<cudaStream_t>(cuda_stream);
   } else {
@@ -543,7 +548,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
 
   // Pass 2: jobs + host->device staging.
   int max_mbs = 0, max_rows = 0, max_cols = 0, max_parts = 1;
-  bool any_inter = false, any_intra = false, any_wave = false, any_tokens = false, any_modes = false;
+  bool any_inter = false, any_intra = false, any_wave = false, any_tokens = false, any_modes = false, any_level_walk = false;
   std::vector<int> level_max;  // per dependency level: most intra MBs of that level in any frame
   size_t at = 0, gather_max = 0;
   std::vector<int> cur_idx(n);
@@ -588,7 +593,11 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
       j.n_inter = int(h.n_inter_mbs);
       j.n_intra = n_mb - j.n_inter;
       j.n_intra_levels = int(h.n_intra_levels);
-      if (h.n_intra_levels) {
+      if (h.n_intra_levels && e->intra_one_launch) {
+        j.intra_levels = reinterpret_cast<const uint32_t *>(j.payload + size_t(h.intra_levels_at) * 16);
+        j.levels_in_one_launch = 1;
+        any_level_walk = true;  // launches IntraLevelsKernel
+      } else if (h.n_intra_levels) {
         j.intra_levels = reinterpret_cast<const uint32_t *>(j.payload + size_t(h.intra_levels_at) * 16);
         if (level_max.size() < h.n_intra_levels) level_max.resize(h.n_intra_levels, 0);
         if (f->blob) {
@@ -666,7 +675,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
       CU_TRY(vp8r::LaunchIntraFlat(sl.d_jobs, n, int(L), level_max[L], e->st));
       e->acc.launches_intra++;
     }
-    if (any_modes) {
+    if (any_modes || any_level_walk) {
       CU_TRY(vp8r::LaunchIntraLevels(sl.d_jobs, n, e->st));
       e->acc.launches_intra++;
     }
