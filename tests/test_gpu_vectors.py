@@ -476,3 +476,37 @@ def test_device_parse_survives_corrupted_streams(engine):
             st.close()
             orc.close()
     assert compared > 40
+
+
+def test_device_parse_4k_segments(engine):
+    """BASELINE config 5 with the device-side parse: a 3840x2160 long-GOP stream cut at its key frames,
+    the segments decoded as independent streams of one batch with macroblock headers and tokens decoded
+    on the GPU; every frame's device checksum equals the host-parsed decode of the unsplit stream."""
+    import vp8_b200
+    from vp8_b200 import shard
+    ivf = helpers.synth_stream("--width 3840 --height 2160 --frames 8 --seed 77 --key-interval 4 --log2-parts 3 --pct-skip 60")
+    _, payloads = vp8_b200.read_ivf(ivf)
+    # reference pass: host parse, one stream
+    want = []
+    ps, st = vp8_b200.Parser(), engine.open_stream()
+    for p in payloads:
+        fr = ps.parse(p, pinned=True)
+        engine.reconstruct_batch([st], [fr])
+        engine.sync()
+        want.append(st.checksum())
+        fr.close()
+    st.close()
+    segs = shard.split_at_key_frames(payloads)
+    assert len(segs) == 2
+    dec = vp8_b200.BatchDecoder(engine, len(segs), pinned=True, device_parse=True, depth=3)
+    got = {g: [] for g in range(len(segs))}
+
+    def on_step(t, live, frames):
+        sums = engine.checksum_batch([dec.streams[i] for i in live])
+        for i, s in zip(live, sums):
+            got[i].append(s)
+
+    dec.decode([s[1] for s in segs], on_step=on_step)
+    dec.close()
+    stitched = [c for g in range(len(segs)) for c in got[g]]
+    assert stitched == want
