@@ -166,7 +166,7 @@ def main():
                          "headers on the GPU for --device-share of the streams and on host threads for the rest")
     ap.add_argument("--device-share", type=float, default=None,
                     help="mix: share of the streams whose macroblock headers are decoded on the GPU "
-                         "(default 1 - 0.5/n_gpus: the host cores are shared by all ranks)")
+                         "(default 1 - 0.4/n_gpus: the host cores are shared by all ranks)")
     ap.add_argument("--serial-setup", action="store_true", help="generate the streams one at a time (for runs under ncu)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -280,7 +280,7 @@ def main():
     for f in (f for fr in resident for f in fr):
         f.close()
     dec.close()
-    device_share = args.device_share if args.device_share is not None else 1.0 - 0.5 / world
+    device_share = args.device_share if args.device_share is not None else 1.0 - 0.4 / world
     # time steps in flight between host parse and the arrival of the frames in host memory (each holds
     # S x 3.1 MB of pinned output; one step less when several ranks share the host's memory)
     DEPTH = 4 if world == 1 else 3

@@ -7,6 +7,7 @@ parsing of step t+1 overlaps the device work of step t; fences guard the reuse o
 """
 import ctypes as C
 import os
+import time
 
 from . import _capi
 from ._capi import check
@@ -88,17 +89,26 @@ class BatchDecoder:
         Returns (frames decoded, frames shown, h2d bytes, d2h bytes)."""
         steps = max(len(p) for p in payloads)
         decoded = shown = h2d = d2h = 0
+        self.host_seconds = {"parse": 0.0, "submit": 0.0, "readback": 0.0, "wait": 0.0, "account": 0.0}
+        hs, clock = self.host_seconds, time.perf_counter
         tickets = {}
         live = [i for i in range(self.n) if len(payloads[i]) > 0]
+        t0 = clock()
         frames = self.parse_step(0, [p[0] if p else b"" for p in payloads], live)
+        hs["parse"] += clock() - t0
         for t in range(steps):
+            t0 = clock()
             streams = [self.streams[i] for i in live]
             self.engine.reconstruct_batch(streams, frames)
+            hs["submit"] += clock() - t0
+            t0 = clock()
             decoded += len(live)
             for f in frames:
                 d = f.desc()
                 h2d += (0 if d.hdr.modes_deferred else d.hdr.mb_cols * d.hdr.mb_rows * 32) + d.hdr.n_payload_blocks * 32
                 shown += d.hdr.show_frame
+            hs["account"] += clock() - t0
+            t0 = clock()
             if out_ring is not None:
                 ring = out_ring[t % self.depth]
                 self.engine.read_batch(streams, [ring[i][0] for i in live], [ring[i][1] for i in live], async_=True)
@@ -108,14 +118,19 @@ class BatchDecoder:
                 self.engine.read_batch_packed(streams, ptrs[t % self.depth], stride, async_=True)
                 d2h += len(streams) * stride
             tickets[t] = self.fence()
+            hs["readback"] += clock() - t0
             if on_step:
                 on_step(t, live, frames)
             if t + 1 < steps:
                 old = t + 1 - self.depth
+                t0 = clock()
                 if old in tickets:
                     self.wait(tickets.pop(old))  # slot and ring entry (t+1) % depth are free again
+                hs["wait"] += clock() - t0
+                t0 = clock()
                 live = [i for i in range(self.n) if len(payloads[i]) > t + 1]
                 frames = self.parse_step((t + 1) % self.depth, [p[t + 1] if len(p) > t + 1 else b"" for p in payloads], live)
+                hs["parse"] += clock() - t0
         self.engine.sync()
         return decoded, shown, h2d, d2h
 

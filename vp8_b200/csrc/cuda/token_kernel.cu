@@ -551,7 +551,10 @@ __device__ void ModeThread(const DevFrameJob &job, const vp8r_token_hdr *th, uns
           for (int k = 0; k < 4; ++k) above_sub[c * 4 + k] = mbmv, left_sub[k] = mbmv;
         }
       }
-      if ((idx & 3) == 3 || idx + 1 == n_mb) {  // the token threads follow a few macroblocks behind
+#ifndef VP8R_MODE_PUBLISH
+#define VP8R_MODE_PUBLISH 4
+#endif
+      if ((idx & (VP8R_MODE_PUBLISH - 1)) == VP8R_MODE_PUBLISH - 1 || idx + 1 == n_mb) {  // the token threads follow a few macroblocks behind
         __threadfence_block();
         *done = idx + 1;
       }
