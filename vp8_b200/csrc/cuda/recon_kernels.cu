@@ -451,12 +451,8 @@ constexpr int kInterWarps = 4;
 #ifndef VP8R_INTER_MINBLOCKS
 #define VP8R_INTER_MINBLOCKS 12  // 40 registers: measured best (8: 64 regs -8 %, 14: 32 regs with spills -10 %)
 #endif
-__global__ void __launch_bounds__(kInterWarps * 32, VP8R_INTER_MINBLOCKS) InterKernel(const DevFrameJob *__restrict__ jobs) {
-  __shared__ InterScratch s_scratch[kInterWarps];
-  const DevFrameJob &job = jobs[blockIdx.y];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mb_index = blockIdx.x * kInterWarps + warp;
-  if (JobInter(job) == 0 || mb_index >= job.mb_cols * job.mb_rows) return;
+// One inter macroblock by one warp.
+__device__ __forceinline__ void InterOneMacroblock(const DevFrameJob &job, int mb_index, int lane, InterScratch &scratch) {
   vp8r_mb_info mb;
   {
     const int4 *p = reinterpret_cast<const int4 *>(job.mbs + mb_index);
@@ -468,7 +464,6 @@ __global__ void __launch_bounds__(kInterWarps * 32, VP8R_INTER_MINBLOCKS) InterK
   if (!(mb.flags & VP8R_MB_IS_INTER)) return;
 
   int res[16];
-  InterScratch &scratch = s_scratch[warp];
   const bool has_res = WarpResidual(job, mb, lane, scratch.y2, res);
   const int mb_r = mb_index / job.mb_cols, mb_c = mb_index - mb_r * job.mb_cols;
   const bool split = ((mb.flags >> VP8R_MB_MODE_SHIFT) & 7) == 4;
@@ -611,8 +606,31 @@ __global__ void __launch_bounds__(kInterWarps * 32, VP8R_INTER_MINBLOCKS) InterK
   }
 }
 
+// Macroblocks per warp.  Walking several consecutive macroblocks per warp (shared record lines,
+// overlapping reference windows) was measured and is much slower: 4 per warp 3.8x, 8 per warp 10.8x
+// the time of 1 per warp (the loop body spills ~300 bytes per thread and the warp's serial latency
+// chain gets longer while nothing else hides it).
+#ifndef VP8R_INTER_MBS_PER_WARP
+#define VP8R_INTER_MBS_PER_WARP 1
+#endif
+constexpr int kInterMbsPerWarp = VP8R_INTER_MBS_PER_WARP;
+__global__ void __launch_bounds__(kInterWarps * 32, VP8R_INTER_MINBLOCKS) InterKernel(const DevFrameJob *__restrict__ jobs) {
+  __shared__ InterScratch s_scratch[kInterWarps];
+  const DevFrameJob &job = jobs[blockIdx.y];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (JobInter(job) == 0) return;
+  const int n_mb = job.mb_cols * job.mb_rows;
+  const int first = (blockIdx.x * kInterWarps + warp) * kInterMbsPerWarp;
+  for (int k = 0; k < kInterMbsPerWarp; ++k) {
+    if (first + k >= n_mb) break;
+    InterOneMacroblock(job, first + k, lane, s_scratch[warp]);
+    __syncwarp();  // the scratch is rewritten by the next macroblock
+  }
+}
+
 cudaError_t LaunchInter(const DevFrameJob *jobs, int n_frames, int max_mbs, cudaStream_t st) {
-  dim3 grid((max_mbs + kInterWarps - 1) / kInterWarps, n_frames);
+  const int per_cta = kInterWarps * kInterMbsPerWarp;
+  dim3 grid((max_mbs + per_cta - 1) / per_cta, n_frames);
   InterKernel<<<grid, kInterWarps * 32, 0, st>>>(jobs);
   return cudaGetLastError();
 }
