@@ -607,9 +607,9 @@ __device__ __forceinline__ void InterOneMacroblock(const DevFrameJob &job, int m
 }
 
 // Macroblocks per warp.  Walking several consecutive macroblocks per warp (shared record lines,
-// overlapping reference windows) was measured and is much slower: 4 per warp 3.8x, 8 per warp 10.8x
-// the time of 1 per warp (the loop body spills ~300 bytes per thread and the warp's serial latency
-// chain gets longer while nothing else hides it).
+// overlapping reference windows) was measured and is slower: 2 per warp +23 %, 4 per warp +30 % of the
+// time of 1 per warp (the loop body spills ~200 bytes per thread and the warp's serial latency chain
+// gets longer); letting the compiler unroll that loop blows the instruction cache (4 per warp 3.8x).
 #ifndef VP8R_INTER_MBS_PER_WARP
 #define VP8R_INTER_MBS_PER_WARP 1
 #endif
@@ -621,6 +621,7 @@ __global__ void __launch_bounds__(kInterWarps * 32, VP8R_INTER_MINBLOCKS) InterK
   if (JobInter(job) == 0) return;
   const int n_mb = job.mb_cols * job.mb_rows;
   const int first = (blockIdx.x * kInterWarps + warp) * kInterMbsPerWarp;
+#pragma unroll 1
   for (int k = 0; k < kInterMbsPerWarp; ++k) {
     if (first + k >= n_mb) break;
     InterOneMacroblock(job, first + k, lane, s_scratch[warp]);
