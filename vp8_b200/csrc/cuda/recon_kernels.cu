@@ -304,9 +304,13 @@ __device__ __forceinline__ unsigned AddResidual4(unsigned pred, unsigned r01, un
   return se | (so << 8);
 }
 
+// Word index of luma row r in InterScratch::hl: rows are 4 words; every 8 rows one row is skipped so
+// that the vertical pass (lanes read rows k, k+2, ..., k+14 at once) hits 8 different bank groups.
+__device__ __forceinline__ int HlRow(int r) { return (r + (r >> 3)) * 4; }
+
 // Per-warp scratch of the macroblock-level motion compensation.
 struct __align__(16) InterScratch {
-  unsigned hl[21 * 4];     // luma after the horizontal pass: 21 rows x 16 pixels
+  unsigned hl[23 * 4];     // luma after the horizontal pass: 21 rows x 16 pixels, row r at word HlRow(r)
   unsigned hc[2][13 * 2];  // U, V after the horizontal pass: 13 rows x 8 pixels
   short res[24][16];       // residual of the 24 blocks
   short y2[16];
@@ -371,7 +375,7 @@ __device__ __forceinline__ void InterMacroblockWhole(const DevFrameJob &job, con
         if (row >= r_lo && row < r_hi) {
           const unsigned lo = __funnelshift_r(lw[k][0], lw[k][1], shift), mid = __funnelshift_r(lw[k][1], lw[k][2], shift),
                          hi = lw[k][2] >> shift;
-          s.hl[row * 4 + w] = fc ? Filter4P(lo, mid, hi, t03, t45) : __funnelshift_r(lo, mid, 16);
+          s.hl[HlRow(row) + w] = fc ? Filter4P(lo, mid, hi, t03, t45) : __funnelshift_r(lo, mid, 16);
         }
       }
     }
@@ -399,7 +403,7 @@ __device__ __forceinline__ void InterMacroblockWhole(const DevFrameJob &job, con
       unsigned e[7], o[7];
 #pragma unroll
       for (int k = 0; k < 7; ++k) {
-        const unsigned r = s.hl[(y0 + k) * 4 + w];
+        const unsigned r = s.hl[HlRow(y0 + k) + w];
         e[k] = __byte_perm(r, 0, 0x4240);
         o[k] = __byte_perm(r, 0, 0x4341);
       }
@@ -407,8 +411,8 @@ __device__ __forceinline__ void InterMacroblockWhole(const DevFrameJob &job, con
       out0 = Vert6(e, o, t);
       out1 = Vert6(e + 1, o + 1, t);
     } else {
-      out0 = s.hl[(y0 + 2) * 4 + w];
-      out1 = s.hl[(y0 + 3) * 4 + w];
+      out0 = s.hl[HlRow(y0 + 2) + w];
+      out1 = s.hl[HlRow(y0 + 3) + w];
     }
     if (has_res) {
       const uint2 *rp = reinterpret_cast<const uint2 *>(&s.res[(y0 >> 2) * 4 + w][(y0 & 3) * 4]);

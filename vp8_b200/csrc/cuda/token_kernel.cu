@@ -679,28 +679,36 @@ __global__ void __launch_bounds__((kTokenWarps + 1) * 32) TokenKernel(const DevF
         unsigned stored = 0;
         int16_t *out = coef_area + (size_t)(row_base + stored_row) * 16;
         const int ytype = has_y2 ? 0 : 3, yfirst = has_y2 ? 1 : 0;
+        // Neighbour contexts as two bit sets indexed by block: ca / cl bit b = "the block above / to the
+        // left of block b is non-zero".  Seeded with the neighbouring macroblocks' flags for the blocks on
+        // the top row / left column of each plane; inside the macroblock a non-zero block sets the bits of
+        // the blocks below and to the right of it (raw flags, src/bitstream_parser.cc:500-534).
+        unsigned ca = ((abv >> 8) & 1u) | ((abv & 0xfu) << 1) | (((abv >> 4) & 3u) << 17) | (((abv >> 6) & 3u) << 21);
+        unsigned cl = ((left >> 8) & 1u) | ((left & 1u) << 1) | (((left >> 1) & 1u) << 5) | (((left >> 2) & 1u) << 9) |
+                      (((left >> 3) & 1u) << 13) | (((left >> 4) & 1u) << 17) | (((left >> 5) & 1u) << 19) |
+                      (((left >> 6) & 1u) << 21) | (((left >> 7) & 1u) << 23);
+        constexpr unsigned kInnerAboveY = 0x0001ffe0u, kInnerAboveC = (3u << 19) | (3u << 23);  // blocks whose upper neighbour is in this MB
+        constexpr unsigned kInnerLeft = 0x0001dddcu | (1u << 18) | (1u << 20) | (1u << 22) | (1u << 24);  // ... left neighbour
+        const unsigned char *const pb_y2 = sh.probs + ((1 * 8 + 0) * 3) * 11;
+        const unsigned char *const pb_y = sh.probs + ((ytype * 8 + yfirst) * 3) * 11;  // band of coefficient `first` is `first`
+        const unsigned char *const pb_uv = sh.probs + ((2 * 8 + 0) * 3) * 11;
         for (int b = has_y2 ? 0 : 1; b < 25; ++b) {
-          // block kind, neighbour contexts (inside the macroblock: raw flags, src/bitstream_parser.cc:500-534)
-          int type, first, dc_f, ac_f, a, l;
+          const int ctx = (int)(((ca >> b) & 1u) + ((cl >> b) & 1u));
+          const unsigned char *p = (b == 0 ? pb_y2 : (b <= 16 ? pb_y : pb_uv)) + ctx * 11;
+          if (!bd.Bit(p[0])) continue;
+          int type, first, dc_f, ac_f;
           if (b == 0) {
             type = 1; first = 0; dc_f = dq[VP8R_DQ_Y2_DC]; ac_f = dq[VP8R_DQ_Y2_AC];
-            a = (int)((abv >> 8) & 1); l = (int)((left >> 8) & 1);
           } else if (b <= 16) {
-            const int i = (b - 1) >> 2, j = (b - 1) & 3;
             type = ytype; first = yfirst; dc_f = dq[VP8R_DQ_Y1_DC]; ac_f = dq[VP8R_DQ_Y1_AC];
-            a = (int)(((i ? raw_nz >> (b - 4) : abv >> j)) & 1);
-            l = (int)(((j ? raw_nz >> (b - 1) : left >> i)) & 1);
           } else {
-            const int k = (b - 17) & 3, cshift = 4 + 2 * ((b - 17) >> 2), i = k >> 1, j = k & 1;
             type = 2; first = 0; dc_f = dq[VP8R_DQ_UV_DC]; ac_f = dq[VP8R_DQ_UV_AC];
-            a = (int)(((i ? raw_nz >> (b - 2) : abv >> (cshift + j))) & 1);
-            l = (int)(((j ? raw_nz >> (b - 1) : left >> (cshift + i))) & 1);
           }
-          const unsigned char *p = sh.probs + ((type * 8 + first) * 3 + a + l) * 11;  // band of coefficient `first` is `first`
-          if (!bd.Bit(p[0])) continue;
-          const int res = ReadTokens(bd, sh.probs, type, a + l, first, dc_f, ac_f, blk);
+          const int res = ReadTokens(bd, sh.probs, type, ctx, first, dc_f, ac_f, blk);
           if (res & 1) {
             raw_nz |= 1u << b;
+            ca |= b <= 16 ? (16u << b) & kInnerAboveY : (4u << b) & kInnerAboveC;
+            cl |= (2u << b) & kInnerLeft;
             uint4 lo = *reinterpret_cast<const uint4 *>(blk), hi = *reinterpret_cast<const uint4 *>(blk + 8);
             *reinterpret_cast<uint4 *>(out + stored * 16) = lo;
             *reinterpret_cast<uint4 *>(out + stored * 16 + 8) = hi;

@@ -410,8 +410,14 @@ void FrameParser::ParseInterMb(int r, int c, int idx, int ref, vp8r_mb_info *mb,
       const Mv zero{0, 0};
       for (int part = 0; part < kSplitCount[layout]; ++part) {
         int k = kSplitHead[layout][part];
-        Mv lmv = (k & 3) ? sub[k - 1] : (c == 0 ? zero : sub_mvs_[size_t(idx - 1) * 16 + k + 3]);
-        Mv amv = (k >= 4) ? sub[k - 4] : (r == 0 ? zero : sub_mvs_[size_t(idx - mb_cols_) * 16 + k + 12]);
+        // a neighbouring macroblock's sub-block vector: stored only for SPLIT macroblocks, otherwise
+        // its one vector (zero for intra macroblocks)
+        auto neighbour = [&](int i, int b) {
+          const MbCtx &m = mbctx_[i];
+          return (m.is_inter && m.mode == MV_SPLIT) ? sub_mvs_[size_t(i) * 16 + b] : m.mv;
+        };
+        Mv lmv = (k & 3) ? sub[k - 1] : (c == 0 ? zero : neighbour(idx - 1, k + 3));
+        Mv amv = (k >= 4) ? sub[k - 4] : (r == 0 ? zero : neighbour(idx - mb_cols_, k + 12));
         int ctx;  // src/inter_predict.h:42-43, src/inter_predict.cc:112-114
         if (lmv == amv) ctx = amv.nonzero() ? 3 : 4;
         else if (!amv.nonzero()) ctx = 2;
@@ -434,8 +440,6 @@ void FrameParser::ParseInterMb(int r, int c, int idx, int ref, vp8r_mb_info *mb,
       break;
     }
   }
-  if (!*split)
-    for (int b = 0; b < 16; ++b) sub[b] = mbmv;
 
   mbctx_[idx] = MbCtx{1, uint8_t(ref), uint8_t(mode), mbmv};
   mb->flags |= VP8R_MB_IS_INTER | (uint32_t(ref) << VP8R_MB_REF_SHIFT) | (uint32_t(mode) << VP8R_MB_MODE_SHIFT);
@@ -463,7 +467,7 @@ int FrameParser::ParseMacroblocks(vp8r_frame *out) {
   vp8r_frame_hdr &h = out->hdr;
 
   mbctx_.assign(n_mb, MbCtx{0, 0, 0, Mv{0, 0}});
-  if (!key_frame_) sub_mvs_.assign(n_mb * 16, Mv{0, 0});
+  if (!key_frame_ && sub_mvs_.size() < n_mb * 16) sub_mvs_.resize(n_mb * 16);  // written for SPLIT macroblocks only
   above_bmodes_.assign(size_t(cols) * 4, B_DC);
   nz_above_y_.assign(size_t(cols) * 4, 0);
   nz_above_u_.assign(size_t(cols) * 2, 0);
