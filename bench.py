@@ -297,6 +297,7 @@ def main():
         decoded, shown, h2d, d2h = e2e_dec.decode(payloads, out_packed=packed)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    host_seconds = {k: round(v, 3) for k, v in getattr(e2e_dec, "host_seconds", {}).items()}  # last pass, this rank
     e2e_sums = eng.checksum_batch(e2e_dec.streams)
     if e2e_sums != sums:
         raise SystemExit("bench: device-resident replay and end-to-end pass disagree on the final frames")
@@ -338,7 +339,7 @@ def main():
                     "kernel_ms_per_step": (tm2.ms_inter + tm2.ms_intra + tm2.ms_filter) / max(1, args.e2e_steps + 1),
                     "token_kernel_ms_per_step": tm2.ms_tokens / max(1, args.e2e_steps + 1),
                     "parse": args.e2e_parse, "device_header_share": device_share if args.e2e_parse == "mix" else None,
-                    "steps_in_flight": DEPTH},
+                    "steps_in_flight": DEPTH, "host_seconds_last_pass": host_seconds},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
