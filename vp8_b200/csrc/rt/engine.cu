@@ -310,6 +310,27 @@ void DrainTimers(vp8r_engine *e) {
   e->live.clear();
 }
 
+// Scratch job tables of the read-back / checksum paths (kPackBufs parts) and the checksum words.
+int EnsureScratchJobs(vp8r_engine *e, int n) {
+  if (n <= e->cap_cjobs) return VP8R_OK;
+  CU_TRY(cudaStreamSynchronize(e->st));
+  if (e->h_cjobs) cudaFreeHost(e->h_cjobs);
+  if (e->d_cjobs) cudaFree(e->d_cjobs);
+  if (e->h_sums) cudaFreeHost(e->h_sums);
+  if (e->d_sums) cudaFree(e->d_sums);
+  e->h_cjobs = e->d_cjobs = nullptr;
+  e->h_sums = e->d_sums = nullptr;
+  e->cap_cjobs = 0;
+  const int cap = std::max(n, 64);
+  const size_t table = sizeof(DevFrameJob) * cap * vp8r_engine::kPackBufs + 16;
+  CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_cjobs), table, cudaHostAllocDefault));
+  CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_cjobs), table));
+  CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_sums), sizeof(uint64_t) * cap, cudaHostAllocDefault));
+  CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_sums), sizeof(uint64_t) * cap));
+  e->cap_cjobs = cap;
+  return VP8R_OK;
+}
+
 void FillJobSurfaces(const vp8r_stream *s, int cur, DevFrameJob *j) {
   j->cur = s->surf[cur].planes;
   for (int k = 1; k < 4; ++k) j->ref[k] = s->ref[k] >= 0 ? s->surf[s->ref[k]].planes : vp8r::DevPlanes{};
@@ -462,6 +483,7 @@ VP8R_API int vp8r_stream_open(vp8r_engine *e, vp8r_stream **out) {
 VP8R_API void vp8r_stream_close(vp8r_stream *s) {
   if (!s) return;
   cudaSetDevice(s->eng->device);
+  cudaStreamSynchronize(s->eng->st_parse);  // a parse kernel may still use the stream's segment map
   cudaStreamSynchronize(s->eng->st);
   FreeSurfaces(s);
   delete s->own_frame;
@@ -792,22 +814,8 @@ VP8R_API int vp8r_read_batch_packed(vp8r_engine *e, int n, vp8r_stream *const *s
     CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_pack), vp8r_engine::kPackBufs * half + 256));
     e->pack_cap = half;
   }
-  // job table: reuse the checksum scratch, growing it if needed
-  if (n > e->cap_cjobs) {
-    CU_TRY(cudaStreamSynchronize(e->st));
-    if (e->h_cjobs) cudaFreeHost(e->h_cjobs);
-    if (e->d_cjobs) cudaFree(e->d_cjobs);
-    if (e->h_sums) cudaFreeHost(e->h_sums);
-    if (e->d_sums) cudaFree(e->d_sums);
-    e->h_cjobs = e->d_cjobs = nullptr;
-    e->h_sums = e->d_sums = nullptr;
-    int cap = std::max(n, 64);
-    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_cjobs), sizeof(DevFrameJob) * cap * vp8r_engine::kPackBufs + 16, cudaHostAllocDefault));
-    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_cjobs), sizeof(DevFrameJob) * cap * vp8r_engine::kPackBufs + 16));
-    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_sums), sizeof(uint64_t) * cap, cudaHostAllocDefault));
-    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_sums), sizeof(uint64_t) * cap));
-    e->cap_cjobs = cap;
-  }
+  rc = EnsureScratchJobs(e, n);
+  if (rc) return rc;
   // kPackBufs parts of the job table and of the staging buffer rotate: the pack kernel of this call
   // runs on the engine's stream while the D2H copy of the previous call may still be in flight on
   // the copy stream.
@@ -856,21 +864,10 @@ VP8R_API int vp8r_checksum_batch(vp8r_engine *e, int n, vp8r_stream *const *stre
   if (!e || n <= 0 || !streams || !out) return VP8R_ERR_INVALID_ARG;
   int rc = EnsureDevice(e);
   if (rc) return rc;
-  if (n > e->cap_cjobs) {
-    CU_TRY(cudaStreamSynchronize(e->st));
-    if (e->h_cjobs) cudaFreeHost(e->h_cjobs);
-    if (e->d_cjobs) cudaFree(e->d_cjobs);
-    if (e->h_sums) cudaFreeHost(e->h_sums);
-    if (e->d_sums) cudaFree(e->d_sums);
-    e->h_cjobs = e->d_cjobs = nullptr;
-    e->h_sums = e->d_sums = nullptr;
-    int cap = std::max(n, 64);
-    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_cjobs), sizeof(DevFrameJob) * cap * vp8r_engine::kPackBufs + 16, cudaHostAllocDefault));
-    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_cjobs), sizeof(DevFrameJob) * cap * vp8r_engine::kPackBufs + 16));
-    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->h_sums), sizeof(uint64_t) * cap, cudaHostAllocDefault));
-    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_sums), sizeof(uint64_t) * cap));
-    e->cap_cjobs = cap;
-  }
+  // synchronous call: nothing queued may still read part 0 of the scratch job table
+  CU_TRY(cudaStreamSynchronize(e->st));
+  rc = EnsureScratchJobs(e, n);
+  if (rc) return rc;
   for (int i = 0; i < n; ++i) {
     const vp8r_stream *s = streams[i];
     if (!s || s->eng != e || !s->have_frame) {
