@@ -48,12 +48,27 @@ class BatchDecoder:
         for p in self.parsers:
             p.reset()
 
+    @staticmethod
+    def _payload_pointers(payloads, live):
+        """Array of pointers to the compressed frames.  `bytes` objects are passed in place (the parser
+        only reads them during the call); anything else is copied into a ctypes buffer first.  Returns
+        (pointer array, objects to keep alive until the call returns)."""
+        keep, ptrs = [], []
+        for i in live:
+            p = payloads[i]
+            if isinstance(p, bytes):
+                ptrs.append(C.cast(C.c_char_p(p), C.c_void_p))
+            else:
+                buf = (C.c_uint8 * max(len(p), 1)).from_buffer_copy(bytes(p) or b"\0")
+                keep.append(buf)
+                ptrs.append(C.cast(buf, C.c_void_p))
+        return (C.c_void_p * len(ptrs))(*ptrs), keep
+
     def parse_step(self, slot, payloads, live):
         """Parses payloads[i] (bytes) of the live streams into slot `slot`.  Returns the frames."""
         n = len(live)
-        bufs = [(C.c_uint8 * len(payloads[i])).from_buffer_copy(payloads[i]) for i in live]
         pa = (C.c_void_p * n)(*[self.parsers[i].handle for i in live])
-        da = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
+        da, keep = self._payload_pointers(payloads, live)
         sa = (C.c_size_t * n)(*[len(payloads[i]) for i in live])
         frames = [self.slots[slot][i] for i in live]
         fa = (C.c_void_p * n)(*[f.handle for f in frames])
@@ -63,9 +78,8 @@ class BatchDecoder:
     def parse_into(self, frames, payloads, live):
         """Parses payloads[i] of the live streams into caller-owned ParsedFrame objects (host threads)."""
         n = len(live)
-        bufs = [(C.c_uint8 * len(payloads[i])).from_buffer_copy(payloads[i]) for i in live]
         pa = (C.c_void_p * n)(*[self.parsers[i].handle for i in live])
-        da = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
+        da, keep = self._payload_pointers(payloads, live)
         sa = (C.c_size_t * n)(*[len(payloads[i]) for i in live])
         fa = (C.c_void_p * n)(*[f.handle for f in frames])
         check(self._lib.vp8r_parse_batch(n, pa, da, sa, fa, self.parse_threads, None))
