@@ -234,3 +234,33 @@ def test_deferred_token_parse_matches_full_parse(built):
                 at += th.part_size[k]
             a.close()
             b.close()
+
+
+def test_deferred_parse_falls_back_for_huge_frames(built):
+    """Frames with more than 65536 macroblocks are parsed on the host even when deferral was asked for
+    (the device parse kernel keeps two bytes per macroblock in shared memory)."""
+    import vp8_b200
+    data = helpers.synth_stream("--width 4112 --height 4112 --frames 1 --seed 2 --log2-parts 1 --pct-skip 90")
+    _, payloads = vp8_b200.read_ivf(data)
+    full, lazy = vp8_b200.Parser(), vp8_b200.Parser()
+    lazy.set_defer_modes(True)
+    a, b = full.parse(payloads[0]), lazy.parse(payloads[0])
+    da, db = a.desc(), b.desc()
+    assert da.hdr.mb_cols * da.hdr.mb_rows == 257 * 257 > 65536
+    assert db.hdr.tokens_deferred == 0 and db.hdr.modes_deferred == 0
+    assert db.hdr.n_payload_blocks == da.hdr.n_payload_blocks and db.hdr.n_coef_blocks == da.hdr.n_coef_blocks
+    n = da.hdr.mb_cols * da.hdr.mb_rows
+    assert all(da.mbs[i].flags == db.mbs[i].flags and da.mbs[i].coef_mask == db.mbs[i].coef_mask for i in range(0, n, 97))
+    a.close()
+    b.close()
+
+
+def test_batch_payload_pointers_in_place(built):
+    """BatchDecoder hands `bytes` payloads to the parser without copying; other buffer types are copied."""
+    import ctypes as C
+    from vp8_b200.batch import BatchDecoder
+    p0, p1 = b"\x01\x02\x03\x04", bytearray(b"\x09\x08\x07")
+    ptrs, keep = BatchDecoder._payload_pointers([p0, p1, b""], [0, 1, 2])
+    assert len(ptrs) == 3 and len(keep) == 1
+    assert C.string_at(ptrs[0], 4) == p0 and C.string_at(ptrs[1], 3) == bytes(p1)
+    assert ptrs[0] == C.cast(C.c_char_p(p0), C.c_void_p).value  # the bytes object's own buffer
