@@ -11,7 +11,9 @@ of a GPU once.  Streams are independent, so N GPUs = N*S streams, no collective 
   e2e   : frames/s through the public API from compressed frames in host memory to cropped I420
           in pinned host memory: host parse + H2D + kernels + D2H inside the timed region
   roofline : algorithmic bytes (1.5*Wa*Ha*(1+is_inter) + 32*coded blocks per frame)
-          over the device time of the reconstruction kernels, against MEASURED_PEAKS.json hbm_gbs
+          over the device time of ALL reconstruction kernels, against MEASURED_PEAKS.json hbm_gbs;
+          roofline.per_kernel gives the same bytes attributed to the loop filter / motion compensation
+          over that kernel's own device time (per launch = one batch of S frames)
   cpu_baseline : the reference decoder (oracle/_ref/decode, compiled unmodified from the
           reference sources) on the host cores, one process per stream, on a bounded sample
 
@@ -274,6 +276,19 @@ def main():
                 "kernel_ms": {k: round(v, 3) for k, v in shares.items()},
                 "dominant_avg_launch_ms": shares[dominant] / max(1, n_launch[dominant]),
                 "alg_bytes_per_frame": tm.alg_bytes / max(1, tm.frames)}
+    # per-kernel view: the same algorithmic bytes attributed to the kernel that moves them (the loop filter
+    # reads and writes every frame once; motion compensation reads one reference frame, writes the frame
+    # and reads the coded coefficients), over that kernel's own device time
+    plane_bytes = 1.5 * W * ((H + 15) // 16 * 16)
+    n_inter_frames = tm.frames * (FRAMES - 1) / FRAMES
+    per_kernel = {}
+    for name, alg, ms_k in (("filter", tm.frames * 2 * plane_bytes, tm.ms_filter),
+                            ("inter", n_inter_frames * 2 * plane_bytes + 32.0 * tm.coef_blocks, tm.ms_inter)):
+        if ms_k > 0:
+            a = alg / (ms_k / 1e3) / 1e9
+            per_kernel[name] = {"achieved": a, "frac": a / peak, "alg_bytes_per_launch": alg / max(1, n_launch[name]),
+                                "avg_launch_ms": ms_k / max(1, n_launch[name])}
+    roofline["per_kernel"] = per_kernel
     launches = tm.launches_inter + tm.launches_intra + tm.launches_filter
 
     # ---- end to end: compressed frames in host memory -> cropped I420 in pinned host memory ----
