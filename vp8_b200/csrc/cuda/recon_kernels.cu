@@ -1304,7 +1304,13 @@ __global__ void __launch_bounds__(kFiltWarps * 32, kFiltCtasPerSm) FilterKernel(
 }
 
 cudaError_t LaunchFilter(const DevFrameJob *jobs, int n_frames, int max_rows, int *sync, int sync_ints,
-                         cudaStream_t st) {
+                         cudaStream_t st, const FilterGroup *groups, int n_groups) {
+  if (groups && n_groups > 0) {
+    cudaError_t e = LaunchFilterSwar(jobs, groups, n_groups, max_rows, sync, sync_ints, st);
+    if (e != cudaSuccess) return e;
+    BorderKernel<<<dim3(8, n_frames), 256, 0, st>>>(jobs);
+    return cudaGetLastError();
+  }
   // Bands: one warp per macroblock row (8-warp CTAs pack 4 per SM at 64 registers); with few frames
   // in the batch, thinner bands put more SMs to work.
   int n_bands = (max_rows + kFiltWarps - 1) / kFiltWarps;

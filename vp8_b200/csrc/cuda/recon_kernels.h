@@ -88,10 +88,23 @@ cudaError_t LaunchInter(const DevFrameJob *jobs, int n_frames, int max_mbs, cuda
 cudaError_t LaunchIntra(const DevFrameJob *jobs, int n_frames, int max_rows, cudaStream_t st);
 // Flat intra: every intra MB of dependency level `level` (frames with n_intra_levels > 0).
 cudaError_t LaunchIntraFlat(const DevFrameJob *jobs, int n_frames, int level, int max_count, cudaStream_t st);
+// Up to eight frames with the same geometry and filter type (and a non-zero frame filter level) that one
+// warp of the batch loop filter walks together; unused slots are -1, slot 0 is always used.
+struct FilterGroup {
+  int frame[8];
+};
 // K_filter: normal/simple loop filter as a per-frame macroblock wavefront, then border extension.
 // `sync`: device scratch of `sync_ints` ints (ticket + one progress word per (frame, band)).
+// With `groups` (device pointer, n_groups > 0) the batch form runs (filter_swar.cu: four pixel lines per
+// register, eight frames per warp); without, the scalar form (one warp per macroblock row of one frame),
+// which has the shorter latency per frame.
 cudaError_t LaunchFilter(const DevFrameJob *jobs, int n_frames, int max_rows, int *sync, int sync_ints,
-                         cudaStream_t st);
+                         cudaStream_t st, const FilterGroup *groups = nullptr, int n_groups = 0);
+cudaError_t LaunchFilterSwar(const DevFrameJob *jobs, const FilterGroup *groups, int n_groups, int max_rows, int *sync,
+                             int sync_ints, cudaStream_t st);
+void SwarProfDump();  // development aid, see filter_swar.cu (no-op in normal builds)
+// Ints of `sync` scratch LaunchFilter needs for a batch.
+inline int FilterSyncInts(int n_frames) { return 1 + n_frames * 128; }
 // Host->device staging without the copy engines (which the packed read-back keeps busy): `src` is
 // pinned host memory read by the SMs over PCIe.  LaunchCopy moves one buffer (bytes % 16 == 0, both
 // 16-byte aligned); LaunchGather moves every job's blob (h2d_src -> h2d_dst, h2d_bytes).

@@ -128,6 +128,10 @@ struct vp8r_engine {
   // intra scheduling of host-parsed inter frames: one launch per dependency level (default) or one
   // level-walking launch (VP8R_INTRA_ONE_LAUNCH=1)
   bool intra_one_launch = false;
+  // loop filter form: 0 = by batch size (batch form from `swar_min_frames` filtered frames on), 1 = always
+  // the scalar form, 2 = always the batch form (VP8R_FILTER=scalar|swar, VP8R_FILTER_SWAR_MIN=<frames>)
+  int filter_mode = 0;
+  int swar_min_frames = 1 << 30;  // batch form only on request until it wins (see profiles/)
   // timing
   bool timing = false;
   std::vector<EventPair> live;
@@ -242,8 +246,10 @@ int GrowSlot(vp8r_engine *e, Slot &sl, int n_jobs, size_t arena_bytes) {
     if (sl.d_jobs) cudaFree(sl.d_jobs);
     sl.h_jobs = nullptr;
     sl.d_jobs = nullptr;
-    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_jobs), sizeof(DevFrameJob) * cap + 16, cudaHostAllocDefault));
-    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&sl.d_jobs), sizeof(DevFrameJob) * cap + 16));
+    // the batch's filter groups (at most one per job) follow the jobs in the same table
+    const size_t table = (sizeof(DevFrameJob) + sizeof(vp8r::FilterGroup)) * cap + 16;
+    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_jobs), table, cudaHostAllocDefault));
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&sl.d_jobs), table));
     sl.cap_jobs = cap;
   }
   if (arena_bytes > sl.arena_cap) {
@@ -375,6 +381,8 @@ VP8R_API int vp8r_engine_create(int device, void *cuda_stream, vp8r_engine **out
   if (!e) return VP8R_ERR_NOMEM;
   e->device = device;
   if (const char *v = std::getenv("VP8R_INTRA_ONE_LAUNCH")) e->intra_one_launch = v[0] == '1';
+  if (const char *v = std::getenv("VP8R_FILTER")) e->filter_mode = std::strcmp(v, "scalar") == 0 ? 1 : (std::strcmp(v, "swar") == 0 ? 2 : 0);
+  if (const char *v = std::getenv("VP8R_FILTER_SWAR_MIN")) e->swar_min_frames = std::max(1, std::atoi(v));
   if (cuda_stream) {
     e->st = static_cast<cudaStream_t>(cuda_stream);
   } else {
@@ -417,6 +425,7 @@ VP8R_API void vp8r_engine_destroy(vp8r_engine *e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->st);
+  vp8r::SwarProfDump();
   if (e->st_copy) {
     cudaStreamSynchronize(e->st_copy);
     cudaStreamDestroy(e->st_copy);
@@ -573,6 +582,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
   bool any_inter = false, any_intra = false, any_wave = false, any_tokens = false, any_modes = false, any_level_walk = false;
   std::vector<int> level_max;  // per dependency level: most intra MBs of that level in any frame
   size_t at = 0, gather_max = 0;
+  int n_groups = 0;
   std::vector<int> cur_idx(n);
   // Staging and the parse kernel go to the parse stream when any frame has deferred tokens, so that
   // they overlap the reconstruction kernels of the previous time step on `st`.
@@ -672,7 +682,30 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
       e->acc.alg_bytes += uint64_t(n_mb) * 384 * (h.key_frame ? 1 : 2) + uint64_t(h.n_coef_blocks) * 32;
     }
     static_assert(sizeof(DevFrameJob) % 8 == 0, "job table is copied in 16-byte units");
-    CU_TRY(vp8r::LaunchCopy(sl.d_jobs, sl.h_jobs, sizeof(DevFrameJob) * n, front));
+    // Filter groups: frames with the same geometry and filter type, eight to a warp (filter_swar.cu).
+    {
+      std::vector<int> order;
+      for (int i = 0; i < n; ++i)
+        if (frames[i]->hdr.loop_filter_level != 0) order.push_back(i);
+      const bool swar = e->filter_mode == 2 || (e->filter_mode == 0 && int(order.size()) >= e->swar_min_frames);
+      if (swar && !order.empty()) {
+        auto key = [&](int i) {
+          const vp8r_frame_hdr &h = frames[i]->hdr;
+          return (uint64_t(h.mb_cols) << 32) | (uint64_t(h.mb_rows) << 8) | uint64_t(h.filter_type != 0);
+        };
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
+        vp8r::FilterGroup *hg = reinterpret_cast<vp8r::FilterGroup *>(sl.h_jobs + n);
+        for (size_t at_o = 0; at_o < order.size();) {
+          vp8r::FilterGroup g;
+          int k = 0;
+          const uint64_t kk = key(order[at_o]);
+          for (; k < 8 && at_o < order.size() && key(order[at_o]) == kk; ++k, ++at_o) g.frame[k] = order[at_o];
+          for (; k < 8; ++k) g.frame[k] = -1;
+          hg[n_groups++] = g;
+        }
+      }
+    }
+    CU_TRY(vp8r::LaunchCopy(sl.d_jobs, sl.h_jobs, sizeof(DevFrameJob) * n + sizeof(vp8r::FilterGroup) * n_groups, front));
     CU_TRY(vp8r::LaunchGather(sl.d_jobs, n, gather_max, front));
     e->acc.launches_other += 2;
   }
@@ -708,7 +741,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
   }
   {
     ScopedTimer t(e, 2);
-    const int need_sync = 1 + n * 64;
+    const int need_sync = vp8r::FilterSyncInts(n);
     if (need_sync > e->sync_cap) {
       CU_TRY(cudaStreamSynchronize(e->st));
       if (e->d_sync) cudaFree(e->d_sync);
@@ -716,7 +749,8 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
       CU_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_sync), sizeof(int) * size_t(need_sync) * 2));
       e->sync_cap = need_sync * 2;
     }
-    CU_TRY(vp8r::LaunchFilter(sl.d_jobs, n, max_rows, e->d_sync, e->sync_cap, e->st));
+    CU_TRY(vp8r::LaunchFilter(sl.d_jobs, n, max_rows, e->d_sync, e->sync_cap, e->st,
+                              reinterpret_cast<const vp8r::FilterGroup *>(sl.d_jobs + n), n_groups));
     e->acc.launches_filter++;
   }
   CU_TRY(cudaEventRecord(sl.done, e->st));
