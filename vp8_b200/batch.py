@@ -93,13 +93,15 @@ class BatchDecoder:
     def wait(self, ticket):
         check(self._lib.vp8r_engine_wait(self.engine.handle, ticket))
 
-    def decode(self, payloads, out_ring=None, on_step=None, out_packed=None):
+    def decode(self, payloads, out_ring=None, on_step=None, out_packed=None, shown_only=True):
         """payloads[s] = list of compressed frames of stream s.  out_ring: optional list of `depth` lists
         of (ptr, capacity) pinned host buffers, one per stream, that receive the frames of a time step
         (ring of `depth` steps).  out_packed: optional ((ptr0, ptr1, ...), stride): `depth` pinned host
         buffers; the frames of a time step are cropped and packed on the device and arrive with one copy,
-        frame k of the step's live streams at ptr + k*stride.  on_step(t, live, frames) is called after step t
-        has been submitted.
+        frame k of the step's live streams at ptr + k*stride.  shown_only (default): only frames with
+        show_frame set are read back (the reference never writes a hidden frame, src/decode.cc:76), so frame k
+        of the packed buffer is the k-th SHOWN frame of the step.  on_step(t, live, frames) is called after
+        step t has been submitted.
         Returns (frames decoded, frames shown, h2d bytes, d2h bytes)."""
         steps = max(len(p) for p in payloads)
         decoded = shown = h2d = d2h = 0
@@ -117,20 +119,24 @@ class BatchDecoder:
             hs["submit"] += clock() - t0
             t0 = clock()
             decoded += len(live)
-            for f in frames:
+            out_idx = []
+            for k, f in enumerate(frames):
                 d = f.desc()
                 h2d += (0 if d.hdr.modes_deferred else d.hdr.mb_cols * d.hdr.mb_rows * 32) + d.hdr.n_payload_blocks * 32
                 shown += d.hdr.show_frame
+                if d.hdr.show_frame or not shown_only:
+                    out_idx.append(k)
             hs["account"] += clock() - t0
             t0 = clock()
-            if out_ring is not None:
+            if out_ring is not None and out_idx:
                 ring = out_ring[t % self.depth]
-                self.engine.read_batch(streams, [ring[i][0] for i in live], [ring[i][1] for i in live], async_=True)
-                d2h += sum(s.frame_bytes() for s in streams)
-            if out_packed is not None:
+                self.engine.read_batch([streams[k] for k in out_idx], [ring[live[k]][0] for k in out_idx],
+                                       [ring[live[k]][1] for k in out_idx], async_=True)
+                d2h += sum(streams[k].frame_bytes() for k in out_idx)
+            if out_packed is not None and out_idx:
                 (ptrs, stride) = out_packed
-                self.engine.read_batch_packed(streams, ptrs[t % self.depth], stride, async_=True)
-                d2h += len(streams) * stride
+                self.engine.read_batch_packed([streams[k] for k in out_idx], ptrs[t % self.depth], stride, async_=True)
+                d2h += len(out_idx) * stride
             tickets[t] = self.fence()
             hs["readback"] += clock() - t0
             if on_step:

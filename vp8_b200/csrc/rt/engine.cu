@@ -131,7 +131,7 @@ struct vp8r_engine {
   // loop filter form: 0 = by batch size (batch form from `swar_min_frames` filtered frames on), 1 = always
   // the scalar form, 2 = always the batch form (VP8R_FILTER=scalar|swar, VP8R_FILTER_SWAR_MIN=<frames>)
   int filter_mode = 0;
-  int swar_min_frames = 1 << 30;  // batch form only on request until it wins (see profiles/)
+  int swar_min_frames = 128;  // measured: 64 frames 1.22 ms (batch) vs 1.06 (scalar); 256: 1.67 vs 2.23; 512: 2.61 vs 4.11
   // timing
   bool timing = false;
   std::vector<EventPair> live;
