@@ -308,6 +308,68 @@ __device__ __forceinline__ unsigned AddResidual4(unsigned pred, unsigned r01, un
 // that the vertical pass (lanes read rows k, k+2, ..., k+14 at once) hits 8 different bank groups.
 __device__ __forceinline__ int HlRow(int r) { return (r + (r >> 3)) * 4; }
 
+// ---- TMA plumbing (sm_90+): a bulk tensor load of one box into shared memory, completion on an mbarrier ----
+__device__ __forceinline__ unsigned SmemAddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void MbarInit(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SmemAddr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy (the TMA unit)
+}
+__device__ __forceinline__ void MbarExpectTx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void MbarWait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "MBAR_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra MBAR_DONE_%=;\n\t"
+      "bra MBAR_WAIT_%=;\n\t"
+      "MBAR_DONE_%=:\n\t}" ::"r"(SmemAddr(bar)), "r"(parity)
+      : "memory");
+}
+// Box of `map` whose first element is (x, y) -> dst (128-byte aligned shared memory); bytes land on `bar`.
+__device__ __forceinline__ void TmaLoad2D(void *dst, const DevTensorMap *map, int x, int y, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   SmemAddr(dst)),
+               "l"(map), "r"(x), "r"(y), "r"(SmemAddr(bar))
+               : "memory");
+}
+
+// Reference windows of one macroblock as the TMA unit delivers them: dense boxes.
+struct __align__(128) InterTile {
+  unsigned char luma[kTmaLumaBoxH * kTmaLumaBoxW];            // 21 rows x 48 bytes
+  unsigned char pad0[1024 - kTmaLumaBoxH * kTmaLumaBoxW];
+  unsigned char cu[kTmaChromaBoxH * kTmaChromaBoxW];          // 13 rows x 48 bytes
+  unsigned char pad1[640 - kTmaChromaBoxH * kTmaChromaBoxW];
+  unsigned char cv[kTmaChromaBoxH * kTmaChromaBoxW];
+  unsigned char pad2[640 - kTmaChromaBoxH * kTmaChromaBoxW - 8];
+  unsigned long long bar;                                      // one transaction barrier per warp
+};
+static_assert(sizeof(InterTile) == 2304, "tile layout");
+constexpr unsigned kInterTileTxBytes = kTmaLumaBoxH * kTmaLumaBoxW + 2 * kTmaChromaBoxH * kTmaChromaBoxW;
+
+// Motion vectors and window origins of a macroblock with one vector (src/inter_predict.cc:116-144,246-333).
+struct WholeMbGeometry {
+  int fr, fc, cfr, cfc;  // eighth-pel fractions, luma and chroma
+  int wy, wx, cwy, cwx;  // window origins (row, column) in plane coordinates, clamped as a whole into the border
+};
+__device__ __forceinline__ WholeMbGeometry WholeGeometry(const DevFrameJob &job, const vp8r_mb_info &mb, int mb_r, int mb_c) {
+  WholeMbGeometry g;
+  const int mvr = mb.mv[0], mvc = mb.mv[1];
+  const int sr = s16(4 * mvr), sc = s16(4 * mvc);
+  int cmr = (sr >= 0 ? (sr + 4) : (sr - 4)) / 8, cmc = (sc >= 0 ? (sc + 4) : (sc - 4)) / 8;
+  if (job.version == 3) {
+    cmr &= ~7;
+    cmc &= ~7;
+  }
+  g.fr = mvr & 7; g.fc = mvc & 7; g.cfr = cmr & 7; g.cfc = cmc & 7;
+  g.wy = min(max(mb_r * 16 + (mvr >> 3) - 2, -kBorder), job.mb_rows * 16 + kBorder - 21);
+  g.wx = min(max(mb_c * 16 + (mvc >> 3) - 2, -kBorder), job.mb_cols * 16 + kBorder - 21);
+  g.cwy = min(max(mb_r * 8 + (cmr >> 3) - 2, -kBorder), job.mb_rows * 8 + kBorder - 13);
+  g.cwx = min(max(mb_c * 8 + (cmc >> 3) - 2, -kBorder), job.mb_cols * 8 + kBorder - 13);
+  return g;
+}
+
 // Per-warp scratch of the macroblock-level motion compensation.
 struct __align__(16) InterScratch {
   unsigned hl[23 * 4];     // luma after the horizontal pass: 21 rows x 16 pixels, row r at word HlRow(r)
@@ -321,27 +383,57 @@ struct __align__(16) InterScratch {
 // fetched and filtered once per macroblock (21x21 / 13x13) instead of once per 4x4 block (9x9 each):
 // horizontal pass (dp4a on byte-shifted words) into shared memory, vertical pass on packed 16-bit
 // lanes, residual add, store.
+template <bool kTma>
 __device__ __forceinline__ void InterMacroblockWhole(const DevFrameJob &job, const vp8r_mb_info &mb, int mb_r, int mb_c,
-                                                     int lane, InterScratch &s, bool has_res) {
+                                                     int lane, InterScratch &s, bool has_res, const WholeMbGeometry &g,
+                                                     InterTile *tile) {
   const int ref_id = (mb.flags >> VP8R_MB_REF_SHIFT) & 3;
   const int bil = job.version != 0;
-  const int mvr = mb.mv[0], mvc = mb.mv[1];
-  // chroma vector: 4 x the luma vector, rounded away from zero, / 8 (src/inter_predict.cc:116-144)
-  const int sr = s16(4 * mvr), sc = s16(4 * mvc);
-  int cmr = (sr >= 0 ? (sr + 4) : (sr - 4)) / 8, cmc = (sc >= 0 ? (sc + 4) : (sc - 4)) / 8;
-  if (job.version == 3) {
-    cmr &= ~7;
-    cmc &= ~7;
-  }
-  const int fr = mvr & 7, fc = mvc & 7, cfr = cmr & 7, cfc = cmc & 7;
+  const int fr = g.fr, fc = g.fc, cfr = g.cfr, cfc = g.cfc;
 
+  if (kTma) {
+    // ---- horizontal pass on the boxes the TMA unit put into shared memory: the box starts at the window's
+    // first pixel, so every lane reads aligned words; no address arithmetic on the frame, no byte shifting ----
+    MbarWait(&tile->bar, 0);
+    {
+      const int dx = (g.wx + kBorder) & 15;  // the box starts at the window's x rounded down to 16
+      const int w = lane & 3, row0 = lane >> 2, base = (dx >> 2) + w;
+      const unsigned shift = (dx & 3) * 8;
+      const int r_lo = fr ? 0 : 2, r_hi = (fr | fc) ? (fr ? 21 : 18) : 0;  // whole-pel vectors: the rows are read below, in place
+      const int t03 = c_taps[bil][fc][0], t45 = c_taps[bil][fc][1];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int row = row0 + 8 * k;
+        if (row >= r_lo && row < r_hi) {
+          const unsigned *p = reinterpret_cast<const unsigned *>(tile->luma + row * kTmaLumaBoxW) + base;
+          const unsigned w0 = p[0], w1 = p[1], w2 = p[2];
+          const unsigned lo = __funnelshift_r(w0, w1, shift), mid = __funnelshift_r(w1, w2, shift), hi = w2 >> shift;
+          s.hl[HlRow(row) + w] = fc ? Filter4P(lo, mid, hi, t03, t45) : __funnelshift_r(lo, mid, 16);
+        }
+      }
+    }
+    {
+      const int dx = (g.cwx + kBorder) & 15;
+      const int row = lane >> 1, cw_ = lane & 1, base = (dx >> 2) + cw_;
+      const unsigned shift = (dx & 3) * 8;
+      const int r_lo = cfr ? 0 : 2, r_hi = (cfr | cfc) ? (cfr ? 13 : 10) : 0;
+      const int t03 = c_taps[bil][cfc][0], t45 = c_taps[bil][cfc][1];
+      if (row >= r_lo && row < r_hi) {
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+          const unsigned *p = reinterpret_cast<const unsigned *>((pl ? tile->cv : tile->cu) + row * kTmaChromaBoxW) + base;
+          const unsigned w0 = p[0], w1 = p[1], w2 = p[2];
+          const unsigned lo = __funnelshift_r(w0, w1, shift), mid = __funnelshift_r(w1, w2, shift), hi = w2 >> shift;
+          s.hc[pl][row * 2 + cw_] = cfc ? Filter4P(lo, mid, hi, t03, t45) : __funnelshift_r(lo, mid, 16);
+        }
+      }
+    }
+  } else
   // ---- horizontal pass: all window words of this lane are requested first (15 loads in flight), then
   // filtered.  Luma task = (window row, output word), three rounds; chroma: one round per plane. ----
   {
     const int pitch = job.pitch_y, cpitch = job.pitch_c;
-    int wy = mb_r * 16 + (mvr >> 3) - 2, wx = mb_c * 16 + (mvc >> 3) - 2;
-    wy = min(max(wy, -kBorder), job.mb_rows * 16 + kBorder - 21);
-    wx = min(max(wx, -kBorder), job.mb_cols * 16 + kBorder - 21);
+    const int wy = g.wy, wx = g.wx;
     const uint8_t *wp = job.ref[ref_id].y + (ptrdiff_t)wy * pitch + wx;
     const unsigned shift = ((unsigned)(size_t)wp & 3u) * 8;
     const int w = lane & 3, row0 = lane >> 2;
@@ -352,9 +444,7 @@ __device__ __forceinline__ void InterMacroblockWhole(const DevFrameJob &job, con
       const unsigned *p = reinterpret_cast<const unsigned *>(wp - ((size_t)wp & 3)) + row * (pitch >> 2) + w;
       lw[k][0] = p[0]; lw[k][1] = p[1]; lw[k][2] = p[2];
     }
-    int cwy = mb_r * 8 + (cmr >> 3) - 2, cwx = mb_c * 8 + (cmc >> 3) - 2;
-    cwy = min(max(cwy, -kBorder), job.mb_rows * 8 + kBorder - 13);
-    cwx = min(max(cwx, -kBorder), job.mb_cols * 8 + kBorder - 13);
+    const int cwy = g.cwy, cwx = g.cwx;
     const int crow = min(lane >> 1, 12), cw_ = lane & 1;
     const ptrdiff_t coff = (ptrdiff_t)cwy * cpitch + cwx;
     const uint8_t *up = job.ref[ref_id].u + coff, *vp = job.ref[ref_id].v + coff;
@@ -410,6 +500,12 @@ __device__ __forceinline__ void InterMacroblockWhole(const DevFrameJob &job, con
       const int *t = c_taps6[bil][fr];
       out0 = Vert6(e, o, t);
       out1 = Vert6(e + 1, o + 1, t);
+    } else if (kTma && fc == 0) {  // whole-pel: straight from the window the TMA unit delivered
+      const int dx2 = ((g.wx + kBorder) & 15) + 2;
+      const unsigned *p = reinterpret_cast<const unsigned *>(tile->luma + (y0 + 2) * kTmaLumaBoxW) + (dx2 >> 2) + w;
+      const unsigned sh = (dx2 & 3) * 8;
+      out0 = __funnelshift_r(p[0], p[1], sh);
+      out1 = __funnelshift_r(p[kTmaLumaBoxW / 4], p[kTmaLumaBoxW / 4 + 1], sh);
     } else {
       out0 = s.hl[HlRow(y0 + 2) + w];
       out1 = s.hl[HlRow(y0 + 3) + w];
@@ -438,6 +534,10 @@ __device__ __forceinline__ void InterMacroblockWhole(const DevFrameJob &job, con
         o[k] = __byte_perm(r, 0, 0x4341);
       }
       out = Vert6(e, o, c_taps6[bil][cfr]);
+    } else if (kTma && cfc == 0) {
+      const int dx2 = ((g.cwx + kBorder) & 15) + 2;
+      const unsigned *p = reinterpret_cast<const unsigned *>((pl ? tile->cv : tile->cu) + (y + 2) * kTmaChromaBoxW) + (dx2 >> 2) + w;
+      out = __funnelshift_r(p[0], p[1], (dx2 & 3) * 8);
     } else {
       out = h[(y + 2) * 2 + w];
     }
@@ -456,7 +556,8 @@ constexpr int kInterWarps = 4;
 #define VP8R_INTER_MINBLOCKS 12  // 40 registers: measured best (8: 64 regs -8 %, 14: 32 regs with spills -10 %)
 #endif
 // One inter macroblock by one warp.
-__device__ __forceinline__ void InterOneMacroblock(const DevFrameJob &job, int mb_index, int lane, InterScratch &scratch) {
+template <bool kTma>
+__device__ __forceinline__ void InterOneMacroblock(const DevFrameJob &job, int mb_index, int lane, InterScratch &scratch, InterTile *tile) {
   vp8r_mb_info mb;
   {
     const int4 *p = reinterpret_cast<const int4 *>(job.mbs + mb_index);
@@ -467,10 +568,21 @@ __device__ __forceinline__ void InterOneMacroblock(const DevFrameJob &job, int m
   }
   if (!(mb.flags & VP8R_MB_IS_INTER)) return;
 
-  int res[16];
-  const bool has_res = WarpResidual(job, mb, lane, scratch.y2, res);
   const int mb_r = mb_index / job.mb_cols, mb_c = mb_index - mb_r * job.mb_cols;
   const bool split = ((mb.flags >> VP8R_MB_MODE_SHIFT) & 7) == 4;
+  WholeMbGeometry geo{};
+  if (!split) {
+    geo = WholeGeometry(job, mb, mb_r, mb_c);
+    if (kTma && lane == 0) {  // the three windows are on their way while the warp computes the residual
+      const DevTensorMap *maps = job.ref_tmap[(mb.flags >> VP8R_MB_REF_SHIFT) & 3];
+      MbarExpectTx(&tile->bar, kInterTileTxBytes);
+      TmaLoad2D(tile->luma, maps + 0, (geo.wx + kBorder) & ~15, geo.wy + kBorder, &tile->bar);
+      TmaLoad2D(tile->cu, maps + 1, (geo.cwx + kBorder) & ~15, geo.cwy + kBorder, &tile->bar);
+      TmaLoad2D(tile->cv, maps + 2, (geo.cwx + kBorder) & ~15, geo.cwy + kBorder, &tile->bar);
+    }
+  }
+  int res[16];
+  const bool has_res = WarpResidual(job, mb, lane, scratch.y2, res);
   if (!split) {  // one vector for the whole macroblock: window fetched and filtered once
     const bool mb_has_res = mb.coef_mask != 0;
     if (mb_has_res && lane < 24) {
@@ -486,7 +598,7 @@ __device__ __forceinline__ void InterOneMacroblock(const DevFrameJob &job, int m
         dst[q] = make_uint4(v[0], v[1], v[2], v[3]);
       }
     }
-    InterMacroblockWhole(job, mb, mb_r, mb_c, lane, scratch, mb_has_res);
+    InterMacroblockWhole<kTma>(job, mb, mb_r, mb_c, lane, scratch, mb_has_res, geo, tile);
     return;
   }
   if (lane >= 24) return;
@@ -618,25 +730,33 @@ __device__ __forceinline__ void InterOneMacroblock(const DevFrameJob &job, int m
 #define VP8R_INTER_MBS_PER_WARP 1
 #endif
 constexpr int kInterMbsPerWarp = VP8R_INTER_MBS_PER_WARP;
+template <bool kTma>
 __global__ void __launch_bounds__(kInterWarps * 32, VP8R_INTER_MINBLOCKS) InterKernel(const DevFrameJob *__restrict__ jobs) {
   __shared__ InterScratch s_scratch[kInterWarps];
+  __shared__ InterTile s_tile[kTma ? kInterWarps : 1];
   const DevFrameJob &job = jobs[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (JobInter(job) == 0) return;
+  if (kTma) {  // every warp fetches one macroblock: its barrier completes phase 0 exactly once
+    if (lane == 0) MbarInit(&s_tile[warp].bar, 1);
+    __syncwarp();
+  }
   const int n_mb = job.mb_cols * job.mb_rows;
   const int first = (blockIdx.x * kInterWarps + warp) * kInterMbsPerWarp;
 #pragma unroll 1
   for (int k = 0; k < kInterMbsPerWarp; ++k) {
     if (first + k >= n_mb) break;
-    InterOneMacroblock(job, first + k, lane, s_scratch[warp]);
+    InterOneMacroblock<kTma>(job, first + k, lane, s_scratch[warp], &s_tile[kTma ? warp : 0]);
     __syncwarp();  // the scratch is rewritten by the next macroblock
   }
 }
 
-cudaError_t LaunchInter(const DevFrameJob *jobs, int n_frames, int max_mbs, cudaStream_t st) {
+cudaError_t LaunchInter(const DevFrameJob *jobs, int n_frames, int max_mbs, cudaStream_t st, bool tma) {
+  static_assert(kInterMbsPerWarp == 1, "the TMA path arms each warp's barrier once");
   const int per_cta = kInterWarps * kInterMbsPerWarp;
   dim3 grid((max_mbs + per_cta - 1) / per_cta, n_frames);
-  InterKernel<<<grid, kInterWarps * 32, 0, st>>>(jobs);
+  if (tma) InterKernel<true><<<grid, kInterWarps * 32, 0, st>>>(jobs);
+  else InterKernel<false><<<grid, kInterWarps * 32, 0, st>>>(jobs);
   return cudaGetLastError();
 }
 

@@ -18,6 +18,19 @@ struct DevPlanes {
   uint8_t *y, *u, *v;  // address of pixel (0,0) of each plane
 };
 
+// TMA descriptor (CUtensorMap: 128 bytes, 64-byte aligned) kept opaque here so that this header needs no
+// driver API.  A surface has three, for its padded Y, U, V planes (element = one byte, x fastest; boxes of
+// kTmaLumaBox / kTmaChromaBox): the reference windows of motion compensation come in as bulk tensor loads.
+struct alignas(128) DevTensorMap {
+  unsigned char opaque[128];
+};
+// The first (fastest) coordinate of a bulk tensor load must be a multiple of 16 BYTES (measured on B200: any
+// other value traps as "illegal instruction", tools/microbench/tma_probe2.cu), so a box starts at the window's
+// x rounded down to 16 and is 48 bytes wide: 15 + 21 <= 48, and 48-byte rows keep the lanes' word reads on
+// distinct shared-memory banks.
+constexpr int kTmaLumaBoxW = 48, kTmaLumaBoxH = 21;     // 21x21 window of a 16x16 block
+constexpr int kTmaChromaBoxW = 48, kTmaChromaBoxH = 13;  // 13x13 window of an 8x8 block
+
 // Per-frame results of the device-side macroblock-header pass (frames with deferred modes): what the
 // host parser would have put into vp8r_frame_hdr.
 struct DevFrameDyn {
@@ -30,6 +43,7 @@ struct DevFrameJob {
   const int16_t *payload;
   DevPlanes cur;
   DevPlanes ref[4];  // indexed by reference frame id 1..3 (last, golden, altref)
+  const DevTensorMap *ref_tmap[4];  // per reference frame: descriptors of its Y, U, V planes (nullptr: no TMA path)
   int pitch_y, pitch_c;
   int mb_cols, mb_rows;
   int n_intra, n_inter;
@@ -83,7 +97,9 @@ cudaError_t LaunchIntraLevels(const DevFrameJob *jobs, int n_frames, cudaStream_
 // Blocks (32 B) of device coefficient area a frame with deferred tokens needs.
 inline size_t TokenCoefBlocks(int mb_cols, int mb_rows) { return size_t(mb_cols) * mb_rows * 25; }
 // K_inter: dequant + IWHT/IDCT + motion compensation + residual add for every inter MB.
-cudaError_t LaunchInter(const DevFrameJob *jobs, int n_frames, int max_mbs, cudaStream_t st);
+// `tma`: reference windows of macroblocks with one motion vector are staged in shared memory by bulk tensor
+// loads (every job must carry ref_tmap); otherwise by 32-bit loads of the lanes.
+cudaError_t LaunchInter(const DevFrameJob *jobs, int n_frames, int max_mbs, cudaStream_t st, bool tma = false);
 // K_intra: dequant + IWHT/IDCT + intra prediction as a per-frame macroblock wavefront.
 cudaError_t LaunchIntra(const DevFrameJob *jobs, int n_frames, int max_rows, cudaStream_t st);
 // Flat intra: every intra MB of dependency level `level` (frames with n_intra_levels > 0).

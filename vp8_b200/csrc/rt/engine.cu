@@ -1,6 +1,7 @@
 // Runtime around the kernels: engine (device, CUDA stream, staging), stream contexts (surface
 // pool + last/golden/altref bookkeeping, the role of ref_frames[] in src/decode.cc:40 and
 // RefreshRefFrames in src/loop.h:19-46), batched submission, read-back, timers, C ABI.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -71,6 +72,7 @@ struct vp8r_stream {
   int pitch_y = 0, pitch_c = 0;
   vp8r::Surface surf[5];
   uint8_t *d_segmap = nullptr;  // persistent segment map (frames with deferred modes), one byte per MB
+  vp8r::DevTensorMap *d_tmaps = nullptr;  // 5 surfaces x (Y, U, V) TMA descriptors of the padded planes
   int ref[4] = {-1, -1, -1, -1};  // surface index of CURRENT(latest), LAST, GOLDEN, ALTREF
   bool have_frame = false;
 };
@@ -130,6 +132,7 @@ struct vp8r_engine {
   bool intra_one_launch = false;
   // loop filter form: 0 = by batch size (batch form from `swar_min_frames` filtered frames on), 1 = always
   // the scalar form, 2 = always the batch form (VP8R_FILTER=scalar|swar, VP8R_FILTER_SWAR_MIN=<frames>)
+  bool inter_tma = true;  // reference windows by TMA (VP8R_INTER=ldg: by the lanes' 32-bit loads)
   int filter_mode = 0;
   int swar_min_frames = 128;  // measured: 64 frames 1.22 ms (batch) vs 1.06 (scalar); 256: 1.67 vs 2.23; 512: 2.61 vs 4.11
   // timing
@@ -153,6 +156,55 @@ void FreeSurfaces(vp8r_stream *s) {
   }
   if (s->d_segmap) cudaFree(s->d_segmap);
   s->d_segmap = nullptr;
+  if (s->d_tmaps) cudaFree(s->d_tmaps);
+  s->d_tmaps = nullptr;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn TensorMapEncoder() {
+  static EncodeTiledFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// One descriptor per padded plane: bytes, x fastest, rows `pitch` apart; box = the motion-compensation window.
+bool EncodePlaneMap(vp8r::DevTensorMap *out, uint8_t *padded_origin, int padded_w, int padded_h, int pitch, int box_w, int box_h) {
+  static_assert(sizeof(vp8r::DevTensorMap) == sizeof(CUtensorMap), "opaque descriptor size");
+  EncodeTiledFn enc = TensorMapEncoder();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {cuuint64_t(padded_w), cuuint64_t(padded_h)};
+  const cuuint64_t strides[1] = {cuuint64_t(pitch)};
+  const cuuint32_t box[2] = {cuuint32_t(box_w), cuuint32_t(box_h)};
+  const cuuint32_t estr[2] = {1, 1};
+  if (enc(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, padded_origin, dims, strides, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  // Drivers up to CUDA 13.1 set a descriptor bit for tensors below 128 KB with which the load traps ("illegal
+  // instruction", measured here with tools/microbench/tma_probe.cu); CUTLASS clears the same bit
+  // (cute/atom/copy_traits_sm90_tma.hpp).
+  static const int driver = [] {
+    int v = 0;
+    if (cudaDriverGetVersion(&v) != cudaSuccess) cudaGetLastError();
+    return v;
+  }();
+  if (driver <= 13010 && size_t(pitch) * padded_h < 131072) {
+    uint64_t w1;
+    std::memcpy(&w1, out->opaque + 8, 8);
+    w1 &= ~(uint64_t(1) << 21);
+    std::memcpy(out->opaque + 8, &w1, 8);
+  }
+  return true;
 }
 
 // Device areas behind a frame's blob that the parse kernel fills (deferred tokens / modes).  All
@@ -216,6 +268,26 @@ int ConfigureStream(vp8r_stream *s, const vp8r_frame_hdr &h) {
     sf.planes.y = sf.base + size_t(B) * s->pitch_y + B;
     sf.planes.u = sf.base + ysz + size_t(B) * s->pitch_c + B;
     sf.planes.v = sf.base + ysz + csz + size_t(B) * s->pitch_c + B;
+  }
+  {  // TMA descriptors of the padded planes (motion compensation fetches its reference windows with them)
+    vp8r::DevTensorMap h_maps[15];
+    bool ok = true;
+    for (int k = 0; k < 5 && ok; ++k) {
+      uint8_t *base = s->surf[k].base;
+      ok = EncodePlaneMap(&h_maps[3 * k + 0], base, s->pitch_y, ha + 2 * B, s->pitch_y, vp8r::kTmaLumaBoxW, vp8r::kTmaLumaBoxH) &&
+           EncodePlaneMap(&h_maps[3 * k + 1], base + ysz, s->pitch_c, ha / 2 + 2 * B, s->pitch_c, vp8r::kTmaChromaBoxW, vp8r::kTmaChromaBoxH) &&
+           EncodePlaneMap(&h_maps[3 * k + 2], base + ysz + csz, s->pitch_c, ha / 2 + 2 * B, s->pitch_c, vp8r::kTmaChromaBoxW, vp8r::kTmaChromaBoxH);
+    }
+    if (ok) {
+      void *p = nullptr;
+      if (cudaMalloc(&p, sizeof(h_maps)) != cudaSuccess) {
+        SetError("cudaMalloc(tensor maps) failed");
+        return VP8R_ERR_NOMEM;
+      }
+      s->d_tmaps = static_cast<vp8r::DevTensorMap *>(p);
+      CU_TRY(cudaMemcpyAsync(p, h_maps, sizeof(h_maps), cudaMemcpyHostToDevice, s->eng->st));
+      CU_TRY(cudaStreamSynchronize(s->eng->st));  // h_maps is on the stack
+    }
   }
   {
     const size_t n_mb = size_t(h.mb_cols) * h.mb_rows;
@@ -339,8 +411,12 @@ int EnsureScratchJobs(vp8r_engine *e, int n) {
 
 void FillJobSurfaces(const vp8r_stream *s, int cur, DevFrameJob *j) {
   j->cur = s->surf[cur].planes;
-  for (int k = 1; k < 4; ++k) j->ref[k] = s->ref[k] >= 0 ? s->surf[s->ref[k]].planes : vp8r::DevPlanes{};
+  for (int k = 1; k < 4; ++k) {
+    j->ref[k] = s->ref[k] >= 0 ? s->surf[s->ref[k]].planes : vp8r::DevPlanes{};
+    j->ref_tmap[k] = (s->ref[k] >= 0 && s->d_tmaps) ? s->d_tmaps + 3 * s->ref[k] : nullptr;
+  }
   j->ref[0] = vp8r::DevPlanes{};
+  j->ref_tmap[0] = nullptr;
   j->pitch_y = s->pitch_y;
   j->pitch_c = s->pitch_c;
   j->mb_cols = s->mb_cols;
@@ -382,6 +458,7 @@ VP8R_API int vp8r_engine_create(int device, void *cuda_stream, vp8r_engine **out
   e->device = device;
   if (const char *v = std::getenv("VP8R_INTRA_ONE_LAUNCH")) e->intra_one_launch = v[0] == '1';
   if (const char *v = std::getenv("VP8R_FILTER")) e->filter_mode = std::strcmp(v, "scalar") == 0 ? 1 : (std::strcmp(v, "swar") == 0 ? 2 : 0);
+  if (const char *v = std::getenv("VP8R_INTER")) e->inter_tma = std::strcmp(v, "ldg") != 0;
   if (const char *v = std::getenv("VP8R_FILTER_SWAR_MIN")) e->swar_min_frames = std::max(1, std::atoi(v));
   if (cuda_stream) {
     e->st = static_cast<cudaStream_t>(cuda_stream);
@@ -721,7 +798,9 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
   }
   if (any_inter) {
     ScopedTimer t(e, 0);
-    CU_TRY(vp8r::LaunchInter(sl.d_jobs, n, max_mbs, e->st));
+    bool tma = e->inter_tma;
+    for (int i = 0; i < n && tma; ++i) tma = streams[i]->d_tmaps != nullptr;
+    CU_TRY(vp8r::LaunchInter(sl.d_jobs, n, max_mbs, e->st, tma));
     e->acc.launches_inter++;
   }
   if (any_intra) {
