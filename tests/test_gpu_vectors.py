@@ -510,3 +510,64 @@ def test_device_parse_4k_segments(engine):
     dec.close()
     stitched = [c for g in range(len(segs)) for c in got[g]]
     assert stitched == want
+
+
+@pytest.mark.parametrize("modes", [False, True], ids=["tokens", "modes+tokens"])
+def test_device_parse_failure_names_and_stops_the_stream(engine, modes):
+    """A frame whose device-side parse runs past a partition is not reconstructed; the error (at the next sync)
+    names the stream of the batch; that stream rejects inter frames until its next key frame, the other stream of
+    the batch decodes on and stays bit-exact."""
+    import vp8_b200
+    from vp8_b200._capi import Vp8rError
+    good = vp8_b200.read_ivf(helpers.synth_stream("--width 320 --height 192 --frames 8 --seed 21 --log2-parts 1"))[1]
+    vict = vp8_b200.read_ivf(helpers.synth_stream("--width 320 --height 192 --frames 8 --seed 22 --log2-parts 1 --key-interval 4"))[1]
+    f = vict[2]
+    first_size = (f[0] | f[1] << 8 | f[2] << 16) >> 5
+    if modes:   # shorten the declared first partition: the macroblock headers run past its end
+        cut = first_size // 2
+        tag = (f[0] | f[1] << 8 | f[2] << 16) & 0x1f | (cut << 5)
+        bad = bytes([tag & 0xff, (tag >> 8) & 0xff, (tag >> 16) & 0xff]) + f[3:3 + cut] + f[3 + first_size:]
+    else:       # drop most of the last DCT partition: its token reader runs past the end
+        bad = f[:len(f) - (len(f) - 3 - first_size) // 3]
+    vict = vict[:2] + [bad] + vict[3:]
+
+    def parser():
+        p = vp8_b200.Parser()
+        (p.set_defer_modes if modes else p.set_defer_tokens)(True)
+        return p
+
+    pg, pv, host, orc = parser(), parser(), vp8_b200.Parser(), helpers.Oracle()
+    sg, sv = engine.open_stream(), engine.open_stream()
+    try:
+        reported = False
+        for t in range(8):
+            want = orc.decode(host.parse(good[t]))
+            fg = pg.parse(good[t], pinned=True)
+            if t == 3 and reported:
+                # the victim is stopped: its inter frame is refused, the good stream goes on alone
+                with pytest.raises(Vp8rError) as e2:
+                    engine.reconstruct_batch([sg, sv], [fg, pv.parse(vict[t], pinned=True)])
+                assert e2.value.code in (4, 5)
+                engine.reconstruct_batch([sg], [fg])
+            elif t < 3 or t >= 4:
+                try:
+                    fv = pv.parse(vict[t], pinned=True)
+                except Vp8rError:
+                    fv = None  # the host part of the parse may already reject the damaged frame
+                if fv is None:
+                    engine.reconstruct_batch([sg], [fg])
+                else:
+                    engine.reconstruct_batch([sg, sv], [fg, fv])
+            try:
+                engine.sync()
+            except Vp8rError as e1:
+                assert t == 2 and e1.code == 4 and "stream 1 of the batch" in str(e1)
+                reported = True
+            assert sg.read_frame() == want, f"good stream, frame {t}"
+        assert reported
+        # from its key frame (frame 4) on the victim decodes again
+        assert sv.frame_bytes() > 0
+    finally:
+        sg.close()
+        sv.close()
+        orc.close()

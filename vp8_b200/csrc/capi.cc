@@ -1,6 +1,9 @@
 // Host-only part of the C ABI: parser, parsed-frame objects, checksums, error reporting.
 // (The engine half lives in rt/engine.cu.)
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cstring>
 #include <new>
 #include <string>
@@ -61,6 +64,65 @@ VP8R_API int vp8r_parser_parse(vp8r_parser *p, const uint8_t *data, size_t size,
   return rc;
 }
 
+namespace {
+// Worker threads of vp8r_parse_batch, kept between calls (a batch decoder calls it once per time step; creating
+// and joining threads every call showed up in the host time of the end-to-end pass).  One job at a time; the
+// calling thread works too.
+class ParsePool {
+ public:
+  static ParsePool &Get() {
+    static ParsePool *pool = new ParsePool();  // never destroyed: worker threads may outlive static destructors
+    return *pool;
+  }
+  // Runs work(tid) on `n_threads` threads (tid 0 = the caller) and returns when all are done.
+  void Run(int n_threads, const std::function<void(int)> &work) {
+    std::lock_guard<std::mutex> serial(run_mutex_);
+    {
+      std::unique_lock<std::mutex> lk(m_);
+      while (int(threads_.size()) < n_threads - 1) {
+        const int tid = int(threads_.size()) + 1;
+        threads_.emplace_back([this, tid] { Loop(tid); });
+        threads_.back().detach();
+      }
+      work_ = &work;
+      want_ = n_threads - 1;
+      pending_ = n_threads - 1;
+      ++generation_;
+    }
+    cv_.notify_all();
+    work(0);
+    std::unique_lock<std::mutex> lk(m_);
+    done_cv_.wait(lk, [this] { return pending_ == 0; });
+    work_ = nullptr;
+  }
+
+ private:
+  void Loop(int tid) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(int)> *w = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return generation_ != seen; });
+        seen = generation_;
+        if (tid <= want_) w = work_;
+      }
+      if (w) {
+        (*w)(tid);
+        std::unique_lock<std::mutex> lk(m_);
+        if (--pending_ == 0) done_cv_.notify_one();
+      }
+    }
+  }
+  std::mutex run_mutex_, m_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<std::thread> threads_;
+  const std::function<void(int)> *work_ = nullptr;
+  int want_ = 0, pending_ = 0;
+  uint64_t generation_ = 0;
+};
+}  // namespace
+
 // Parses n frames of n DIFFERENT streams concurrently (one parser per stream; the bool decoder is
 // serial within a stream, so stream-level parallelism is what the host has).
 VP8R_API int vp8r_parse_batch(int n, vp8r_parser *const *parsers, const uint8_t *const *data, const size_t *sizes,
@@ -82,14 +144,8 @@ VP8R_API int vp8r_parse_batch(int n, vp8r_parser *const *parsers, const uint8_t 
       }
     }
   };
-  if (n_threads <= 1) {
-    work(0);
-  } else {
-    std::vector<std::thread> pool;
-    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
-    work(0);
-    for (auto &t : pool) t.join();
-  }
+  if (n_threads <= 1) work(0);
+  else ParsePool::Get().Run(n_threads, work);
   if (first_err.load() != VP8R_OK)
     for (auto &e : errs)
       if (!e.empty()) vp8r::SetError(e);

@@ -168,8 +168,9 @@ __device__ __forceinline__ void FilterBandSwar(const DevFrameJob *__restrict__ j
   const int pl = NB == 4 ? 0 : (u >> 1);   // chroma: 0 = U, 1 = V
   const int sub = NB == 4 ? u : (u & 1);   // row group (vertical edges) / column group (horizontal edges)
   const int fidx = grp.frame[slot];
-  const bool active = fidx >= 0;
-  const DevFrameJob &job = jobs[active ? fidx : grp.frame[0]];  // idle slots shadow slot 0 and store nothing
+  const bool active = fidx >= 0 && !JobFailed(jobs[fidx]);  // a failed frame rides along like an idle slot
+  // idle slots shadow slot 0 (its loads are in range whatever its records say: they only address its own planes) and store nothing
+  const DevFrameJob &job = jobs[active ? fidx : grp.frame[0]];
   // geometry and filter type are the same for every frame of a group
   const int rows = job.mb_rows, cols = job.mb_cols;
   const bool simple = job.filter_type != 0;

@@ -736,7 +736,7 @@ __global__ void __launch_bounds__(kInterWarps * 32, VP8R_INTER_MINBLOCKS) InterK
   __shared__ InterTile s_tile[kTma ? kInterWarps : 1];
   const DevFrameJob &job = jobs[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (JobInter(job) == 0) return;
+  if (JobFailed(job) || JobInter(job) == 0) return;
   if (kTma) {  // every warp fetches one macroblock: its barrier completes phase 0 exactly once
     if (lane == 0) MbarInit(&s_tile[warp].bar, 1);
     __syncwarp();
@@ -957,7 +957,7 @@ __device__ __forceinline__ void IntraMacroblock(const DevFrameJob &job, int r, i
 __global__ void __launch_bounds__(kWaveWarps * 32) IntraKernel(const DevFrameJob *__restrict__ jobs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const DevFrameJob &job = jobs[blockIdx.x];
-  if (JobIntra(job) == 0 || JobIntraLevels(job) != 0) return;
+  if (JobFailed(job) || JobIntra(job) == 0 || JobIntraLevels(job) != 0) return;
   const int rows = job.mb_rows, cols = job.mb_cols;
   volatile int *progress = reinterpret_cast<volatile int *>(smem_raw);
   unsigned short *lut = reinterpret_cast<unsigned short *>(smem_raw + ((rows * 4 + 15) & ~15));
@@ -993,7 +993,7 @@ __global__ void __launch_bounds__(kFlatWarps * 32) IntraFlatKernel(const DevFram
   __shared__ __align__(16) unsigned short lut[160];
   __shared__ IntraScratch scratch[kFlatWarps];
   const DevFrameJob &job = jobs[blockIdx.y];
-  if (job.dyn || job.levels_in_one_launch || level >= job.n_intra_levels) return;  // handled by IntraLevelsKernel
+  if (JobFailed(job) || job.dyn || job.levels_in_one_launch || level >= job.n_intra_levels) return;  // handled by IntraLevelsKernel
   const unsigned first = __ldg(job.intra_levels + level), end = __ldg(job.intra_levels + level + 1);
   for (int i = threadIdx.x; i < 160; i += blockDim.x) lut[i] = c_bpred_lut[i];
   __syncthreads();
@@ -1013,7 +1013,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32) IntraLevelsKernel(const DevF
   __shared__ __align__(16) unsigned short lut[160];
   __shared__ IntraScratch scratch[kLevelWarps];
   const DevFrameJob &job = jobs[blockIdx.x];
-  if (!job.dyn && !job.levels_in_one_launch) return;
+  if (JobFailed(job) || (!job.dyn && !job.levels_in_one_launch)) return;
   const int n_levels = JobIntraLevels(job);
   if (n_levels == 0) return;
   for (int i = threadIdx.x; i < 160; i += blockDim.x) lut[i] = c_bpred_lut[i];
@@ -1050,11 +1050,14 @@ static size_t IntraSmemBytes(int max_rows) {
 
 cudaError_t LaunchIntra(const DevFrameJob *jobs, int n_frames, int max_rows, cudaStream_t st) {
   size_t smem = IntraSmemBytes(max_rows);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static size_t configured[64] = {};  // per device: the attribute belongs to the (function, device) pair
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t &mark = configured[dev & 63];
+  if (smem > 48 * 1024 && smem > mark) {
     cudaError_t e = cudaFuncSetAttribute(IntraKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
+    mark = smem;
   }
   IntraKernel<<<n_frames, kWaveWarps * 32, smem, st>>>(jobs);
   return cudaGetLastError();
@@ -1184,7 +1187,16 @@ constexpr int kFiltWarps = 4;
 constexpr int kMaxBands = 64;
 constexpr int kBandStride = 8;
 constexpr int kFiltCtasPerSm = 8;  // 72 registers: measured best trade of occupancy (28 warps/SM) against spills
-constexpr int kResidentCtas = 148 * kFiltCtasPerSm;  // FilterKernel CTAs that fit on the chip at once
+
+// Streaming multiprocessors of the current device (148 on a B200).
+static int SmCount() {
+  static int count[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int &c = count[dev & 63];
+  if (c == 0 && cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) c = 148;
+  return c;
+}
 
 constexpr int kTilePitch = 20;  // bytes between tile rows, the same for luma and chroma so that
                                 // every row/column offset below is a compile-time immediate
@@ -1201,7 +1213,7 @@ __device__ __forceinline__ int LoadFlagAcquire(const int *p) {
 }
 
 __global__ void __launch_bounds__(kFiltWarps * 32, kFiltCtasPerSm) FilterKernel(const DevFrameJob *__restrict__ jobs, int n_frames,
-                                                                   int n_bands, int *__restrict__ sync) {
+                                                                   int n_bands, int *__restrict__ sync, int resident_ctas) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_ticket;
   if (threadIdx.x == 0) s_ticket = atomicAdd(&sync[0], 1);
@@ -1211,14 +1223,14 @@ __global__ void __launch_bounds__(kFiltWarps * 32, kFiltCtasPerSm) FilterKernel(
   // b+1 becomes runnable ~1.5 macroblock steps per row after band b), not bands parked on a flag.
   // (When everything is resident at once the order is irrelevant for progress; frame-major then
   // keeps the bands of a frame on neighbouring SMs, which measured ~12 % faster.)
-  const bool band_major = n_frames * n_bands > kResidentCtas;
+  const bool band_major = n_frames * n_bands > resident_ctas;
   const int band = band_major ? s_ticket / n_frames : s_ticket % n_bands;
   const int frame = band_major ? s_ticket - band * n_frames : s_ticket / n_bands;
   const DevFrameJob &job = jobs[frame];
   const int rows = job.mb_rows, cols = job.mb_cols;
   const int rpb = (rows + n_bands - 1) / n_bands;
   const int r0 = band * rpb, r1 = min(rows, r0 + rpb);
-  if (job.lf_level == 0 || r0 >= r1) return;
+  if (job.lf_level == 0 || r0 >= r1 || JobFailed(job)) return;
   int *gflag = sync + 1 + frame * n_bands;  // gflag[b]: macroblocks < gflag[b] of band b's last row are final
   volatile int *lprog = reinterpret_cast<volatile int *>(smem_raw);
   FiltTile *tiles = reinterpret_cast<FiltTile *>(smem_raw + ((rpb * 4 + 15) & ~15));
@@ -1434,14 +1446,14 @@ cudaError_t LaunchFilter(const DevFrameJob *jobs, int n_frames, int max_rows, in
   // Bands: one warp per macroblock row (8-warp CTAs pack 4 per SM at 64 registers); with few frames
   // in the batch, thinner bands put more SMs to work.
   int n_bands = (max_rows + kFiltWarps - 1) / kFiltWarps;
-  while (n_bands < kMaxBands && n_frames * n_bands < 148 * 2 && (max_rows + n_bands) / (n_bands + 1) >= 3) ++n_bands;
+  while (n_bands < kMaxBands && n_frames * n_bands < SmCount() * 2 && (max_rows + n_bands) / (n_bands + 1) >= 3) ++n_bands;
   if (n_bands > kMaxBands) n_bands = kMaxBands;
   if (1 + n_frames * n_bands > sync_ints) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(sync, 0, sizeof(int) * (1 + (size_t)n_frames * n_bands), st);
   if (e != cudaSuccess) return e;
   const int rpb = (max_rows + n_bands - 1) / n_bands;
   size_t smem = ((size_t(rpb) * 4 + 15) & ~size_t(15)) + sizeof(FiltTile) * kFiltWarps;
-  FilterKernel<<<n_frames * n_bands, kFiltWarps * 32, smem, st>>>(jobs, n_frames, n_bands, sync);
+  FilterKernel<<<n_frames * n_bands, kFiltWarps * 32, smem, st>>>(jobs, n_frames, n_bands, sync, SmCount() * kFiltCtasPerSm);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   BorderKernel<<<dim3(8, n_frames), 256, 0, st>>>(jobs);
@@ -1560,7 +1572,7 @@ __global__ void __launch_bounds__(256) GatherKernel(const DevFrameJob *__restric
 cudaError_t LaunchCopy(void *dst, const void *src_pinned, size_t bytes, cudaStream_t st) {
   const size_t n16 = (bytes + 15) / 16;
   if (n16 == 0) return cudaSuccess;
-  const int grid = (int)std::min<size_t>((n16 + 255) / 256, 148 * 4);
+  const int grid = (int)std::min<size_t>((n16 + 255) / 256, size_t(SmCount()) * 4);
   CopyKernel<<<grid, 256, 0, st>>>(static_cast<uint4 *>(dst), static_cast<const uint4 *>(src_pinned), n16);
   return cudaGetLastError();
 }

@@ -77,6 +77,10 @@ struct DevFrameJob {
   DevFrameDyn *dyn;
 };
 
+// A frame whose device-side parse ran past the end of a partition: its records are not trustworthy, so no
+// kernel reconstructs it (the host stops the stream when it collects the word, rt/engine.cu HarvestStatus).
+__device__ __forceinline__ bool JobFailed(const DevFrameJob &j) { return j.status && *reinterpret_cast<const volatile int *>(j.status) != 0; }
+
 // Frame fields that come from the host for host-parsed frames and from the device otherwise.
 __device__ __forceinline__ int JobInter(const DevFrameJob &j) { return j.dyn ? j.dyn->n_inter : j.n_inter; }
 __device__ __forceinline__ int JobIntra(const DevFrameJob &j) { return j.dyn ? j.dyn->n_intra : j.n_intra; }

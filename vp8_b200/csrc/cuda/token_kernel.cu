@@ -92,26 +92,45 @@ __constant__ short c_cat_base[6] = {5, 7, 11, 19, 35, 67};
 // RFC 6386 section 7 boolean decoder, 64-bit left-aligned window refilled 32 bits at a time with
 // aligned loads.  Produces the bit sequence of src/bool_decoder.cc:13-41.
 struct BoolDec {
-  const unsigned *next, *end;  // next aligned word to append / first word past the raw section
+  const unsigned *next, *end;  // next aligned word to append / first word that is not wholly inside the partition
+  unsigned tail_mask;          // bytes of *end that still belong to the partition (little-endian word), 0: none
   unsigned long long win;      // upcoming bits, left aligned
   int avail;                   // valid bits in win
   unsigned range;              // 128..255
   int loaded;                  // bytes appended so far (for the over-read test)
 
+  // The reader sees zeros past the end of ITS partition, like the reference's byte-at-a-time reader and the host
+  // reader do (an over-read must not pick up the next partition's bytes).  `lim` = first byte after the partition;
+  // the raw section is padded to whole words, so the word that holds `lim` may be loaded.
+  __device__ __forceinline__ void Bound(const unsigned char *lim) {
+    const unsigned mis = (unsigned)(size_t)lim & 3u;
+    end = reinterpret_cast<const unsigned *>(lim - mis);
+    tail_mask = mis ? (0xffffffffu >> (32 - 8 * mis)) : 0u;
+  }
+  __device__ __forceinline__ unsigned Word(const unsigned *p) const {
+    if (p < end) return __ldg(p);
+    if (p == end && tail_mask) return __ldg(p) & tail_mask;
+    return 0u;
+  }
+  __device__ __forceinline__ unsigned Byte(const unsigned char *p) const {
+    const unsigned char *lim = reinterpret_cast<const unsigned char *>(end) + (tail_mask ? (32 - __clz(tail_mask)) / 8 : 0);
+    return p < lim ? (unsigned)*p : 0u;
+  }
+
   __device__ __forceinline__ void Refill() {
-    unsigned w = 0;
-    if (next < end) w = __ldg(next);
+    const unsigned w0 = Word(next);
+    unsigned w = w0;
     ++next;
     w = __byte_perm(w, 0, 0x0123);  // big endian
     win |= (unsigned long long)w << (32 - avail);
     avail += 32;
     loaded += 4;
   }
-  __device__ __forceinline__ void Init(const unsigned char *raw, unsigned off, const unsigned *raw_end) {
+  __device__ __forceinline__ void Init(const unsigned char *raw, unsigned off, const unsigned char *lim) {
     const unsigned mis = off & 3u;
     next = reinterpret_cast<const unsigned *>(raw + (off - mis));
-    end = raw_end;
-    unsigned w = next < end ? __ldg(next) : 0u;
+    Bound(lim);
+    unsigned w = Word(next);
     ++next;
     w = __byte_perm(w, 0, 0x0123) << (8 * mis);
     win = (unsigned long long)w << 32;
@@ -123,19 +142,18 @@ struct BoolDec {
   // Resumes a decoder handed over by the host after the frame headers (vp8r_mode_hdr): the window
   // is `value` (8 bits) followed by the raw stream from bit `bitpos` of the partition on.
   __device__ __forceinline__ void InitAt(const unsigned char *raw, unsigned part_off, unsigned bitpos, unsigned value,
-                                         unsigned rng, const unsigned *raw_end) {
+                                         unsigned rng, const unsigned char *lim) {
     unsigned at = part_off + (bitpos >> 3);  // byte offset in the raw section
     const unsigned sub = bitpos & 7u;
-    end = raw_end;
-    const unsigned char *lim = reinterpret_cast<const unsigned char *>(raw_end);
+    Bound(lim);
     win = (unsigned long long)value << 56;
     avail = 8;
-    unsigned b = raw + at < lim ? raw[at] : 0u;
+    unsigned b = Byte(raw + at);
     ++at;
     win |= (unsigned long long)(b & (0xffu >> sub)) << (48 + sub);
     avail += 8 - (int)sub;
     while (at & 3u) {
-      b = raw + at < lim ? raw[at] : 0u;
+      b = Byte(raw + at);
       ++at;
       win |= (unsigned long long)b << (56 - avail);
       avail += 8;
@@ -304,8 +322,7 @@ __device__ void ModeThread(const DevFrameJob &job, const vp8r_token_hdr *th, uns
 
   const unsigned char *raw = reinterpret_cast<const unsigned char *>(th) + sizeof(vp8r_token_hdr);
   BoolDec bd;
-  bd.InitAt(raw, mhp->first_off, mhp->bitpos, mhp->value, mhp->range,
-            reinterpret_cast<const unsigned *>(raw + th->raw_bytes));
+  bd.InitAt(raw, mhp->first_off, mhp->bitpos, mhp->value, mhp->range, raw + mhp->first_off + mhp->first_size);
 
   vp8r_mb_info *mbs = const_cast<vp8r_mb_info *>(job.mbs);
   int16_t *payload = const_cast<int16_t *>(job.payload);
@@ -631,7 +648,7 @@ __global__ void __launch_bounds__((kTokenWarps + 1) * 32) TokenKernel(const DevF
   const unsigned raw_bytes = __ldg(&th->raw_bytes);
   const unsigned part_size = __ldg(&th->part_size[warp]);
   BoolDec bd;
-  bd.Init(raw, __ldg(&th->part_off[warp]), reinterpret_cast<const unsigned *>(raw + raw_bytes));
+  bd.Init(raw, __ldg(&th->part_off[warp]), raw + __ldg(&th->part_off[warp]) + part_size);
   bool used = false;
 
   vp8r_mb_info *mbs = const_cast<vp8r_mb_info *>(job.mbs);
@@ -763,11 +780,15 @@ size_t ParseKernelSmem(int max_cols, int max_mbs, bool modes) { return MakeLayou
 cudaError_t LaunchTokens(const DevFrameJob *jobs, int n_frames, int max_cols, int max_mbs, int max_parts, bool modes,
                          cudaStream_t st) {
   const size_t smem = ParseKernelSmem(max_cols, max_mbs, modes);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  // the attribute belongs to the (function, device) pair: one high-water mark per device
+  static size_t configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t &mark = configured[dev & 63];
+  if (smem > 48 * 1024 && smem > mark) {
     cudaError_t e = cudaFuncSetAttribute(TokenKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
+    mark = smem;
   }
   max_parts = max_parts < 1 ? 1 : (max_parts > kTokenWarps ? kTokenWarps : max_parts);
   TokenKernel<<<n_frames, (max_parts + 1) * 32, smem, st>>>(jobs);

@@ -75,6 +75,7 @@ struct vp8r_stream {
   vp8r::DevTensorMap *d_tmaps = nullptr;  // 5 surfaces x (Y, U, V) TMA descriptors of the padded planes
   int ref[4] = {-1, -1, -1, -1};  // surface index of CURRENT(latest), LAST, GOLDEN, ALTREF
   bool have_frame = false;
+  bool failed = false;  // a device-parsed frame of this stream was truncated: nothing decodes until the next key frame
 };
 
 namespace {
@@ -90,6 +91,11 @@ struct Slot {
   cudaEvent_t done = nullptr;
   cudaEvent_t parsed = nullptr;  // staging + parse kernel of this slot's batch finished (on st_parse)
   bool pending = false;
+  // Device-side parse: one error word per job (mapped pinned host memory; bit 0: a DCT partition was read past
+  // its end, bit 1: the first partition was) and the streams of the batch, so that a failure names its stream.
+  int *h_status = nullptr, *d_status = nullptr;
+  std::vector<vp8r_stream *> batch_streams;
+  bool any_status = false;
 };
 }  // namespace
 
@@ -125,8 +131,8 @@ struct vp8r_engine {
   // host-visible fences (vp8r_engine_fence / vp8r_engine_wait)
   cudaEvent_t fence_ev[16] = {};
   uint64_t fence_head = 0;
-  // device-visible error word written by K_tokens (mapped pinned host memory)
-  int *h_status = nullptr, *d_status = nullptr;
+  // first failure of a device-side parse that has been found but not yet reported
+  std::string deferred_error;
   // intra scheduling of host-parsed inter frames: one launch per dependency level (default) or one
   // level-walking launch (VP8R_INTRA_ONE_LAUNCH=1)
   bool intra_one_launch = false;
@@ -322,6 +328,11 @@ int GrowSlot(vp8r_engine *e, Slot &sl, int n_jobs, size_t arena_bytes) {
     const size_t table = (sizeof(DevFrameJob) + sizeof(vp8r::FilterGroup)) * cap + 16;
     CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_jobs), table, cudaHostAllocDefault));
     CU_TRY(cudaMalloc(reinterpret_cast<void **>(&sl.d_jobs), table));
+    if (sl.h_status) cudaFreeHost(sl.h_status);
+    sl.h_status = sl.d_status = nullptr;
+    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_status), sizeof(int) * cap, cudaHostAllocMapped));
+    CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&sl.d_status), sl.h_status, 0));
+    std::memset(sl.h_status, 0, sizeof(int) * cap);
     sl.cap_jobs = cap;
   }
   if (arena_bytes > sl.arena_cap) {
@@ -409,6 +420,31 @@ int EnsureScratchJobs(vp8r_engine *e, int n) {
   return VP8R_OK;
 }
 
+// Error words of a batch whose kernels have finished: a stream with a truncated frame stops decoding (its frame
+// was not reconstructed, see JobFailed in the kernels) until its next key frame.  Returns the number of failures
+// and describes the first one.
+int HarvestStatus(Slot &sl, std::string *what) {
+  int failures = 0;
+  if (!sl.any_status) return 0;
+  for (size_t i = 0; i < sl.batch_streams.size(); ++i) {
+    const int w = static_cast<volatile int *>(sl.h_status)[i];
+    if (w == 0) continue;
+    sl.h_status[i] = 0;
+    vp8r_stream *s = sl.batch_streams[i];
+    if (s) {
+      s->failed = true;
+      s->have_frame = false;
+      s->ref[0] = s->ref[1] = s->ref[2] = s->ref[3] = -1;
+    }
+    if (failures++ == 0 && what)
+      *what = "stream " + std::to_string(i) + " of the batch: " + ((w & 2) ? "the first partition" : "a DCT partition") +
+              " was read past its end (device-side parse); the stream is stopped until its next key frame";
+  }
+  sl.any_status = false;
+  sl.batch_streams.clear();
+  return failures;
+}
+
 void FillJobSurfaces(const vp8r_stream *s, int cur, DevFrameJob *j) {
   j->cur = s->surf[cur].planes;
   for (int k = 1; k < 4; ++k) {
@@ -480,14 +516,6 @@ VP8R_API int vp8r_engine_create(int device, void *cuda_stream, vp8r_engine **out
     cudaEventCreateWithFlags(&e->pack_done[k], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->copy_done[k], cudaEventDisableTiming);
   }
-  if (cudaHostAlloc(reinterpret_cast<void **>(&e->h_status), sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
-      cudaHostGetDevicePointer(reinterpret_cast<void **>(&e->d_status), e->h_status, 0) != cudaSuccess) {
-    cudaGetLastError();
-    SetError("cudaHostAlloc(status word) failed");
-    vp8r_engine_destroy(e);
-    return VP8R_ERR_CUDA;
-  }
-  *e->h_status = 0;
   err = vp8r::InitKernelTables();
   if (err != cudaSuccess) {
     SetError(std::string("kernel table upload: ") + cudaGetErrorString(err));
@@ -521,6 +549,7 @@ VP8R_API void vp8r_engine_destroy(vp8r_engine *e) {
     if (sl.h_jobs) cudaFreeHost(sl.h_jobs);
     if (sl.d_jobs) cudaFree(sl.d_jobs);
     if (sl.d_arena) cudaFree(sl.d_arena);
+    if (sl.h_status) cudaFreeHost(sl.h_status);
     if (sl.done) cudaEventDestroy(sl.done);
     if (sl.parsed) cudaEventDestroy(sl.parsed);
   }
@@ -530,7 +559,6 @@ VP8R_API void vp8r_engine_destroy(vp8r_engine *e) {
   if (e->d_sums) cudaFree(e->d_sums);
   if (e->d_sync) cudaFree(e->d_sync);
   if (e->d_pack) cudaFree(e->d_pack);
-  if (e->h_status) cudaFreeHost(e->h_status);
   for (auto &ev : e->fence_ev)
     if (ev) cudaEventDestroy(ev);
   DrainTimers(e);
@@ -548,10 +576,14 @@ VP8R_API int vp8r_engine_sync(vp8r_engine *e) {
   CU_TRY(cudaStreamSynchronize(e->st));
   CU_TRY(cudaStreamSynchronize(e->st_copy));
   for (bool &b : e->copy_busy) b = false;
-  for (auto &sl : e->slots) sl.pending = false;
-  if (e->h_status && *static_cast<volatile int *>(e->h_status) != 0) {
-    *e->h_status = 0;
-    SetError("a partition was read past its end (device-side parse)");
+  for (auto &sl : e->slots) {
+    sl.pending = false;
+    std::string what;
+    if (HarvestStatus(sl, &what) && e->deferred_error.empty()) e->deferred_error = what;
+  }
+  if (!e->deferred_error.empty()) {
+    SetError(e->deferred_error);
+    e->deferred_error.clear();
     return VP8R_ERR_TRUNCATED;
   }
   return VP8R_OK;
@@ -571,6 +603,9 @@ VP8R_API void vp8r_stream_close(vp8r_stream *s) {
   cudaSetDevice(s->eng->device);
   cudaStreamSynchronize(s->eng->st_parse);  // a parse kernel may still use the stream's segment map
   cudaStreamSynchronize(s->eng->st);
+  for (auto &sl : s->eng->slots)
+    for (auto &p : sl.batch_streams)
+      if (p == s) p = nullptr;
   FreeSurfaces(s);
   delete s->own_frame;
   delete s;
@@ -626,8 +661,16 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
   int rc = EnsureDevice(e);
   if (rc) return rc;
 
-  // Pass 1: validate, configure surfaces, size the staging arena.
-  size_t arena = 0;
+  // Pass 1: validate everything before anything is changed (a rejected batch leaves every stream as it was),
+  // then configure surfaces and size the staging arena.
+  {
+    std::vector<const vp8r_stream *> seen(streams, streams + n);
+    std::sort(seen.begin(), seen.end());
+    if (std::adjacent_find(seen.begin(), seen.end()) != seen.end()) {
+      SetError("a stream appears twice in one batch (frames of one stream are a dependency chain: one per batch)");
+      return VP8R_ERR_INVALID_ARG;
+    }
+  }
   for (int i = 0; i < n; ++i) {
     vp8r_stream *s = streams[i];
     vp8r_frame *f = frames[i];
@@ -636,12 +679,19 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
       return VP8R_ERR_INVALID_ARG;
     }
     const vp8r_frame_hdr &h = f->hdr;
-    if (h.key_frame) {
-      rc = ConfigureStream(s, h);
-      if (rc) return rc;
-    } else if (!s->have_frame || h.mb_cols != s->mb_cols || h.mb_rows != s->mb_rows) {
+    if (!h.key_frame && (!s->have_frame || h.mb_cols != s->mb_cols || h.mb_rows != s->mb_rows)) {
       SetError("inter frame without matching reference frames");
       return VP8R_ERR_STATE;
+    }
+  }
+  size_t arena = 0;
+  for (int i = 0; i < n; ++i) {
+    vp8r_stream *s = streams[i];
+    vp8r_frame *f = frames[i];
+    if (f->hdr.key_frame) {
+      rc = ConfigureStream(s, f->hdr);
+      if (rc) return rc;
+      s->failed = false;
     }
     if (!(f->d_blob && f->d_device == e->device)) arena += FrameDevExtra(f).total;
   }
@@ -651,8 +701,21 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
     CU_TRY(cudaEventSynchronize(sl.done));
     sl.pending = false;
   }
+  {
+    std::string what;
+    if (HarvestStatus(sl, &what)) {
+      e->deferred_error = what;  // reported by the next vp8r_engine_sync / vp8r_engine_wait
+      for (int i = 0; i < n; ++i)
+        if (streams[i]->failed && !frames[i]->hdr.key_frame) {
+          SetError(what);
+          return VP8R_ERR_TRUNCATED;
+        }
+    }
+  }
   rc = GrowSlot(e, sl, n, arena);
   if (rc) return rc;
+  sl.batch_streams.assign(streams, streams + n);
+  sl.any_status = false;
 
   // Pass 2: jobs + host->device staging.
   int max_mbs = 0, max_rows = 0, max_cols = 0, max_parts = 1;
@@ -726,7 +789,8 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
         uint8_t *wr = const_cast<uint8_t *>(dev_blob);
         j.tok_hdr = reinterpret_cast<const uint8_t *>(j.payload + size_t(h.tokens_at) * 16);
         j.coef_base = uint32_t((x.coef_off - f->mb_bytes()) / 32);
-        j.status = e->d_status;
+        j.status = sl.d_status + i;
+        sl.any_status = true;
         any_tokens = true;
         max_cols = std::max(max_cols, int(h.mb_cols));
         max_parts = std::max(max_parts, f->blob ? int(reinterpret_cast<const vp8r_token_hdr *>(f->payload() + size_t(h.tokens_at) * 16)->n_parts)
@@ -1055,7 +1119,7 @@ VP8R_API int vp8r_engine_wait(vp8r_engine *e, uint64_t ticket) {
     SetError("unknown fence ticket");
     return VP8R_ERR_INVALID_ARG;
   }
-  if (e->fence_head - ticket > 16) return VP8R_OK;  // recycled: a later fence on the same stream was recorded over it
+  // A recycled slot holds a LATER fence of the same streams: waiting for that one covers the old ticket too.
   CU_TRY(cudaEventSynchronize(e->fence_ev[ticket & 15]));
   if (e->fence_has_copy[ticket & 15]) CU_TRY(cudaEventSynchronize(e->fence_copy_ev[ticket & 15]));
   return VP8R_OK;
