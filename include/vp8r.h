@@ -266,6 +266,14 @@ VP8R_API int vp8r_stream_read_frame(vp8r_stream *s, uint8_t *dst, size_t cap);
  * this replaces 3*n pitched copies per time step. */
 VP8R_API int vp8r_read_batch_packed(vp8r_engine *e, int n, vp8r_stream *const *streams, uint8_t *dst,
                                     size_t stride, int async);
+/* Output layouts of the packed read-back.  I420 is what YUV<WRITE>::WriteFrame writes (src/yuv.cc:6-28); NV12
+ * (Y plane, then one plane of interleaved U,V pairs: the layout display engines and hardware encoders take) has
+ * the same number of bytes. */
+#define VP8R_LAYOUT_I420 0
+#define VP8R_LAYOUT_NV12 1
+/* vp8r_read_batch_packed with the layout chosen by the caller. */
+VP8R_API int vp8r_read_batch_packed_as(vp8r_engine *e, int n, vp8r_stream *const *streams, uint8_t *dst,
+                                       size_t stride, int async, int layout);
 
 /* Device-side checksum of the cropped I420 image: low word sum(b_i), high word
  * sum((i+1)*b_i), both mod 2^32, i = byte index in the Y,U,V stream.  For parity checks at sizes

@@ -293,6 +293,16 @@ def test_packed_readback_equals_pitched_readback(engine):
         for k, st in enumerate(streams):
             want = st.read_frame()
             assert raw[k * stride:k * stride + len(want)] == want, sizes[k]
+        # the NV12 option: same Y plane, then U and V samples interleaved
+        engine.read_batch_packed(streams, C.addressof(buf), stride, layout="nv12")
+        raw = bytes(buf)
+        for k, st in enumerate(streams):
+            want = st.read_frame()
+            w, h = st.dims()
+            cn = ((w + 1) // 2) * ((h + 1) // 2)
+            u, v = want[w * h:w * h + cn], want[w * h + cn:]
+            nv12 = want[:w * h] + bytes(b for pair in zip(u, v) for b in pair)
+            assert raw[k * stride:k * stride + len(want)] == nv12, sizes[k]
     finally:
         for st in streams:
             st.close()

@@ -1516,7 +1516,8 @@ __global__ void __launch_bounds__(256) PackKernel(const DevFrameJob *__restrict_
   const int wy4 = (w + 3) / 4, wc4 = (cw + 3) / 4;
   const int items_y = wy4 * h, items_c = wc4 * ch;
   const int total = items_y + 2 * items_c;
-  const bool y_vec = (w & 3) == 0, c_vec = (cw & 3) == 0 && ((size_t)w * h & 3) == 0 && ((size_t)cw * ch & 3) == 0;
+  const bool nv12 = job.pack_layout == VP8R_LAYOUT_NV12;
+  const bool y_vec = (w & 3) == 0, c_vec = !nv12 && (cw & 3) == 0 && ((size_t)w * h & 3) == 0 && ((size_t)cw * ch & 3) == 0;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     const uint8_t *src;
     uint8_t *d;
@@ -1539,6 +1540,12 @@ __global__ void __launch_bounds__(256) PackKernel(const DevFrameJob *__restrict_
       d = dst + (size_t)w * h + (size_t)plane * cw * ch + (size_t)row * cw + x;
       n = min(4, cw - x);
       vec = c_vec;
+      if (nv12) {  // U and V samples alternate: this item's bytes go to every second byte of the UV plane
+        const unsigned v = *reinterpret_cast<const unsigned *>(src);
+        uint8_t *uv = dst + (size_t)w * h + ((size_t)row * cw + x) * 2 + plane;
+        for (int k = 0; k < n; ++k) uv[2 * k] = (uint8_t)(v >> (8 * k));
+        continue;
+      }
     }
     const unsigned v = *reinterpret_cast<const unsigned *>(src);
     if (vec && (((size_t)d & 3) == 0)) {

@@ -52,7 +52,8 @@ struct DevFrameJob {
   int16_t dq[4][6];
   uint8_t key_frame, version, filter_type, lf_level, sharpness;
   uint8_t levels_in_one_launch;  // host-built level table walked by IntraLevelsKernel instead of one launch per level
-  uint8_t pad[2];
+  uint8_t pack_layout;           // PackKernel: VP8R_LAYOUT_I420 / VP8R_LAYOUT_NV12
+  uint8_t pad[1];
   // output side (crop / checksum)
   int width, height;
   unsigned long long *checksum;  // optional: receives the I420 checksum

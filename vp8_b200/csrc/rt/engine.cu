@@ -966,7 +966,12 @@ VP8R_API int vp8r_read_batch(vp8r_engine *e, int n, vp8r_stream *const *streams,
 
 VP8R_API int vp8r_read_batch_packed(vp8r_engine *e, int n, vp8r_stream *const *streams, uint8_t *dst, size_t stride,
                                     int async) {
-  if (!e || n <= 0 || !streams || !dst) return VP8R_ERR_INVALID_ARG;
+  return vp8r_read_batch_packed_as(e, n, streams, dst, stride, async, VP8R_LAYOUT_I420);
+}
+
+VP8R_API int vp8r_read_batch_packed_as(vp8r_engine *e, int n, vp8r_stream *const *streams, uint8_t *dst, size_t stride,
+                                       int async, int layout) {
+  if (!e || n <= 0 || !streams || !dst || (layout != VP8R_LAYOUT_I420 && layout != VP8R_LAYOUT_NV12)) return VP8R_ERR_INVALID_ARG;
   int rc = EnsureDevice(e);
   if (rc) return rc;
   for (int i = 0; i < n; ++i) {
@@ -1010,6 +1015,7 @@ VP8R_API int vp8r_read_batch_packed(vp8r_engine *e, int n, vp8r_stream *const *s
     std::memset(&j, 0, sizeof(j));
     FillJobSurfaces(streams[i], streams[i]->ref[0], &j);
     j.pack_dst = stage + size_t(i) * stride;
+    j.pack_layout = uint8_t(layout);
   }
   {
     ScopedTimer t(e, 4);

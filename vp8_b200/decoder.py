@@ -111,12 +111,13 @@ class Engine:
         ca = (C.c_size_t * n)(*caps)
         check(self._lib.vp8r_read_batch(self.handle, n, sa, pa, ca, 1 if async_ else 0))
 
-    def read_batch_packed(self, streams, dst_ptr, stride, async_=False):
+    def read_batch_packed(self, streams, dst_ptr, stride, async_=False, layout="i420"):
         """Device-side crop + pack of every stream's latest frame, one contiguous D2H copy:
-        frame i at dst_ptr + i*stride."""
+        frame i at dst_ptr + i*stride.  layout: "i420" (Y, U, V planes) or "nv12" (Y, interleaved UV)."""
         n = len(streams)
         sa = (C.c_void_p * n)(*[s.handle for s in streams])
-        check(self._lib.vp8r_read_batch_packed(self.handle, n, sa, C.c_void_p(dst_ptr), stride, 1 if async_ else 0))
+        check(self._lib.vp8r_read_batch_packed_as(self.handle, n, sa, C.c_void_p(dst_ptr), stride, 1 if async_ else 0,
+                                                  {"i420": 0, "nv12": 1}[layout]))
 
     def sync(self):
         check(self._lib.vp8r_engine_sync(self.handle))
