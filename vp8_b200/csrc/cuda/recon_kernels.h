@@ -62,8 +62,9 @@ struct DevFrameJob {
   // and the frame's device coefficient area (first block index relative to `payload`)
   const uint8_t *tok_hdr;
   uint32_t coef_base;
-  int *status;                   // device-visible error word (bit 0: a DCT partition was over-read,
-                                 // bit 1: the first partition was)
+  int *status;                   // error word of this job in DEVICE memory (bit 0: a DCT partition was over-read,
+                                 // bit 1: the first partition was): read by every reconstruction kernel
+  int *status_host;              // the same word in mapped pinned host memory, for the host (written on failure only)
   // deferred modes: vp8r_mode_hdr inside the payload; `mbs` then points at a device area the parse
   // kernel fills, as are the SPLIT motion vectors (first block index relative to `payload`), the
   // intra level table and `dyn`; the segment map persists per stream

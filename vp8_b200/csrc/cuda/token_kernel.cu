@@ -25,6 +25,8 @@
 // follow it through a shared progress counter.  Replaces ParseMacroblocks / ParseInterMb /
 // BuildIntraLevels of host/frame_parser.cc, i.e. src/bitstream_parser.cc:320-464,539-568,
 // src/inter_predict.cc:8-244, src/intra_predict.cc:176-183 of the reference.
+#include <cstdlib>
+
 #include "recon_kernels.h"
 
 namespace vp8r {
@@ -92,29 +94,24 @@ __constant__ short c_cat_base[6] = {5, 7, 11, 19, 35, 67};
 // RFC 6386 section 7 boolean decoder, 64-bit left-aligned window refilled 32 bits at a time with
 // aligned loads.  Produces the bit sequence of src/bool_decoder.cc:13-41.
 struct BoolDec {
-  const unsigned *next, *end;  // next aligned word to append / first word that is not wholly inside the partition
-  unsigned tail_mask;          // bytes of *end that still belong to the partition (little-endian word), 0: none
+  const unsigned *next, *end;  // next aligned word to append / first word without a byte of the partition
   unsigned long long win;      // upcoming bits, left aligned
   int avail;                   // valid bits in win
   unsigned range;              // 128..255
   int loaded;                  // bytes appended so far (for the over-read test)
 
-  // The reader sees zeros past the end of ITS partition, like the reference's byte-at-a-time reader and the host
-  // reader do (an over-read must not pick up the next partition's bytes).  `lim` = first byte after the partition;
-  // the raw section is padded to whole words, so the word that holds `lim` may be loaded.
+  // The reader is bounded to ITS partition at word granularity: past the last word that holds partition bytes it
+  // sees zeros, like the reference's byte-at-a-time reader and the host reader (it must not walk into the next
+  // partition).  Up to three bytes behind the end may come from the neighbour inside that last word; they cannot
+  // reach a decision of a frame that is kept: a reader that needs them has consumed more bytes than the partition
+  // has, which BytesConsumed() reports and which stops the frame (JobFailed).  A mask for those bytes was
+  // measured: +8 % parse-kernel time for the extra compare at every refill site.
   __device__ __forceinline__ void Bound(const unsigned char *lim) {
-    const unsigned mis = (unsigned)(size_t)lim & 3u;
-    end = reinterpret_cast<const unsigned *>(lim - mis);
-    tail_mask = mis ? (0xffffffffu >> (32 - 8 * mis)) : 0u;
+    end = reinterpret_cast<const unsigned *>(lim + ((4u - ((unsigned)(size_t)lim & 3u)) & 3u));
   }
-  __device__ __forceinline__ unsigned Word(const unsigned *p) const {
-    if (p < end) return __ldg(p);
-    if (p == end && tail_mask) return __ldg(p) & tail_mask;
-    return 0u;
-  }
+  __device__ __forceinline__ unsigned Word(const unsigned *p) const { return p < end ? __ldg(p) : 0u; }
   __device__ __forceinline__ unsigned Byte(const unsigned char *p) const {
-    const unsigned char *lim = reinterpret_cast<const unsigned char *>(end) + (tail_mask ? (32 - __clz(tail_mask)) / 8 : 0);
-    return p < lim ? (unsigned)*p : 0u;
+    return p < reinterpret_cast<const unsigned char *>(end) ? (unsigned)*p : 0u;
   }
 
   __device__ __forceinline__ void Refill() {
@@ -603,14 +600,21 @@ __device__ void ModeThread(const DevFrameJob &job, const vp8r_token_hdr *th, uns
   dyn->n_intra = (int)n_intra;
   dyn->n_intra_levels = (int)n_levels;
   dyn->n_split = (int)n_split;
-  if (bd.BytesConsumed() > (int)mhp->first_size && job.status) atomicOr(job.status, 2);
+  if (bd.BytesConsumed() > (int)mhp->first_size && job.status) {
+    atomicOr(job.status, 2);
+    if (job.status_host) atomicOr(job.status_host, 2);
+  }
 }
 
 // Block = (most DCT partitions of any frame in the batch + 1) warps; the mode thread is the last warp.
 // Only one lane per warp works, but registers are allocated for all 32: the trimmed block keeps a
 // batch's footprint small enough to share the SMs with the reconstruction kernels of the previous
 // time step.  (A register cap was tried: spills in the serial chain cost more than the occupancy won.)
-__global__ void __launch_bounds__((kTokenWarps + 1) * 32) TokenKernel(const DevFrameJob *__restrict__ jobs) {
+// kBlockWarps / kMinBlocks: launch bounds.  Frames with up to four DCT partitions run in 160-thread blocks that
+// may be capped to 56 registers (seven frames per SM instead of five): that only pays when more frames are in
+// flight than five per SM hold (VP8R_TOKEN_MINBLOCKS, measured in profiles/r2_summary.md).
+template <int kBlockWarps, int kMinBlocks>
+__global__ void __launch_bounds__(kBlockWarps * 32, kMinBlocks) TokenKernel(const DevFrameJob *__restrict__ jobs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const DevFrameJob &job = jobs[blockIdx.x];
   if (!job.tok_hdr) return;
@@ -764,7 +768,10 @@ __global__ void __launch_bounds__((kTokenWarps + 1) * 32) TokenKernel(const DevF
       }
     }
   }
-  if (used && bd.BytesConsumed() > (int)part_size && job.status) atomicOr(job.status, 1);
+  if (used && bd.BytesConsumed() > (int)part_size && job.status) {
+    atomicOr(job.status, 1);
+    if (job.status_host) atomicOr(job.status_host, 1);
+  }
 }
 
 cudaError_t InitParseTables() {
@@ -781,17 +788,24 @@ cudaError_t LaunchTokens(const DevFrameJob *jobs, int n_frames, int max_cols, in
                          cudaStream_t st) {
   const size_t smem = ParseKernelSmem(max_cols, max_mbs, modes);
   // the attribute belongs to the (function, device) pair: one high-water mark per device
-  static size_t configured[64] = {};
+  max_parts = max_parts < 1 ? 1 : (max_parts > kTokenWarps ? kTokenWarps : max_parts);
+  static const int min_blocks = [] { const char *v = std::getenv("VP8R_TOKEN_MINBLOCKS"); return v ? std::atoi(v) : 0; }();
+  const int variant = max_parts <= 4 ? (min_blocks >= 8 ? 3 : (min_blocks >= 7 ? 2 : (min_blocks >= 6 ? 1 : 0))) : 0;
+  void (*kernel)(const DevFrameJob *) = variant == 3   ? TokenKernel<5, 8>
+                                         : variant == 2 ? TokenKernel<5, 7>
+                                         : variant == 1 ? TokenKernel<5, 6>
+                                                        : TokenKernel<kTokenWarps + 1, 0>;
+  // the attribute belongs to the (function, device) pair: one high-water mark per device and variant
+  static size_t configured[64][4] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  size_t &mark = configured[dev & 63];
+  size_t &mark = configured[dev & 63][variant];
   if (smem > 48 * 1024 && smem > mark) {
-    cudaError_t e = cudaFuncSetAttribute(TokenKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     mark = smem;
   }
-  max_parts = max_parts < 1 ? 1 : (max_parts > kTokenWarps ? kTokenWarps : max_parts);
-  TokenKernel<<<n_frames, (max_parts + 1) * 32, smem, st>>>(jobs);
+  kernel<<<n_frames, (max_parts + 1) * 32, smem, st>>>(jobs);
   return cudaGetLastError();
 }
 

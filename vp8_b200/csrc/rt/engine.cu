@@ -93,7 +93,8 @@ struct Slot {
   bool pending = false;
   // Device-side parse: one error word per job (mapped pinned host memory; bit 0: a DCT partition was read past
   // its end, bit 1: the first partition was) and the streams of the batch, so that a failure names its stream.
-  int *h_status = nullptr, *d_status = nullptr;
+  int *h_status = nullptr, *d_status = nullptr;  // mapped pinned host memory and its device alias: the host's copy
+  int *d_status_dev = nullptr;                   // device memory: what the kernels poll (never PCIe)
   std::vector<vp8r_stream *> batch_streams;
   bool any_status = false;
 };
@@ -333,6 +334,9 @@ int GrowSlot(vp8r_engine *e, Slot &sl, int n_jobs, size_t arena_bytes) {
     CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_status), sizeof(int) * cap, cudaHostAllocMapped));
     CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&sl.d_status), sl.h_status, 0));
     std::memset(sl.h_status, 0, sizeof(int) * cap);
+    if (sl.d_status_dev) cudaFree(sl.d_status_dev);
+    sl.d_status_dev = nullptr;
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&sl.d_status_dev), sizeof(int) * cap));
     sl.cap_jobs = cap;
   }
   if (arena_bytes > sl.arena_cap) {
@@ -550,6 +554,7 @@ VP8R_API void vp8r_engine_destroy(vp8r_engine *e) {
     if (sl.d_jobs) cudaFree(sl.d_jobs);
     if (sl.d_arena) cudaFree(sl.d_arena);
     if (sl.h_status) cudaFreeHost(sl.h_status);
+    if (sl.d_status_dev) cudaFree(sl.d_status_dev);
     if (sl.done) cudaEventDestroy(sl.done);
     if (sl.parsed) cudaEventDestroy(sl.parsed);
   }
@@ -789,7 +794,8 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
         uint8_t *wr = const_cast<uint8_t *>(dev_blob);
         j.tok_hdr = reinterpret_cast<const uint8_t *>(j.payload + size_t(h.tokens_at) * 16);
         j.coef_base = uint32_t((x.coef_off - f->mb_bytes()) / 32);
-        j.status = sl.d_status + i;
+        j.status = sl.d_status_dev + i;
+        j.status_host = sl.d_status + i;
         sl.any_status = true;
         any_tokens = true;
         max_cols = std::max(max_cols, int(h.mb_cols));
@@ -852,6 +858,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
   }
 
   if (any_tokens) {
+    CU_TRY(cudaMemsetAsync(sl.d_status_dev, 0, sizeof(int) * n, front));
     ScopedTimer t(e, 5, front);
     CU_TRY(vp8r::LaunchTokens(sl.d_jobs, n, max_cols, max_mbs, max_parts, any_modes, front));
     e->acc.launches_other++;
