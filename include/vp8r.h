@@ -97,7 +97,7 @@ typedef struct vp8r_frame_hdr {
   uint8_t refresh_last, refresh_golden, refresh_altref; /* key frames: all 1 */
   uint8_t copy_to_golden, copy_to_altref;               /* 0 none, 1 last, 2 other (loop.h:19-46) */
   uint8_t sign_bias_golden, sign_bias_altref;
-  uint8_t reserved0[1];
+  uint8_t q_index;            /* quantiser index of the frame (y_ac_qi, 0..127) */
   uint8_t modes_deferred;     /* 1: see modes_at below (implies tokens_deferred) */
   uint8_t tokens_deferred;    /* 1: see tokens_at below */
   int16_t dq[4][6];           /* dequant factors per segment (row 0 only when segmentation is off) */
@@ -274,6 +274,25 @@ VP8R_API int vp8r_read_batch_packed(vp8r_engine *e, int n, vp8r_stream *const *s
 /* vp8r_read_batch_packed with the layout chosen by the caller. */
 VP8R_API int vp8r_read_batch_packed_as(vp8r_engine *e, int n, vp8r_stream *const *streams, uint8_t *dst,
                                        size_t stride, int async, int layout);
+
+/* ---- encoder (the reference only sketches one: src/encode_frame.cc:30-244,
+ * src/residual.cc:5-40,96-108, src/dct.cc:5-65, src/quantizer.cc:5-8; its encode.cc does not compile) ----
+ *
+ * vp8r_encode_key_frames: one KEY frame for each of n different streams, all of size width x height, from cropped
+ * I420 images in host memory (i420[k]: Y, U, V planes back to back, as vp8r_stream_read_frame delivers them).  On the
+ * device, per macroblock and in a closed loop: 16x16 luma and chroma intra mode by squared error (candidates V, H,
+ * DC, TM in that order, a later one only when strictly better: PickIntraModeLuma / PickIntraModeChroma), residual,
+ * forward DCT / WHT, quantisation by the factors of q_index, and the decoder's reconstruction + loop filter, so that
+ * stream k afterwards holds exactly the frame a decoder makes of the result (vp8r_stream_read_frame returns it, and
+ * inter frames decoded next predict from it).  out[k] receives the macroblock records and coefficient blocks (the
+ * same structure the parser produces); vp8r_frame_write_bitstream turns it into a VP8 frame.  Synchronous. */
+VP8R_API int vp8r_encode_key_frames(vp8r_engine *e, int n, vp8r_stream *const *streams, const uint8_t *const *i420,
+                                    int width, int height, int q_index, int loop_filter_level, int sharpness,
+                                    vp8r_frame *const *out);
+/* The inverse of vp8r_parser_parse for key frames: serialises f (key frame, intra macroblocks, one quantiser) into a
+ * VP8 frame with one DCT partition and the default token probabilities.  *size receives the number of bytes needed;
+ * VP8R_ERR_INVALID_ARG when cap is too small (call again) or the frame cannot be written. */
+VP8R_API int vp8r_frame_write_bitstream(const vp8r_frame *f, uint8_t *dst, size_t cap, size_t *size);
 
 /* Device-side checksum of the cropped I420 image: low word sum(b_i), high word
  * sum((i+1)*b_i), both mod 2^32, i = byte index in the Y,U,V stream.  For parity checks at sizes

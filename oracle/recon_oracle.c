@@ -642,3 +642,6 @@ size_t oracle_write_i420(const oracle_decoder *d, uint8_t *dst, size_t cap) {
   for (int r = 0; r < chh; r++, dst += cw) memcpy(dst, f->v + (size_t)r * f->cs, (size_t)cw);
   return need;
 }
+
+/* ------------------------------------------------------------------ encoder side (row f4) ---- */
+#include "enc_oracle.c"

@@ -39,6 +39,16 @@ size_t oracle_write_i420(const oracle_decoder *d, uint8_t *dst, size_t cap);
 void oracle_idct4x4(int16_t blk[16]);
 void oracle_iwht4x4(int16_t blk[16]);
 
+/* Encoder side, see enc_oracle.c.  PINNED on tests/golden/enc/enc_goldens.json. */
+void oracle_fdct4x4(int16_t blk[16]);
+void oracle_fwht4x4(int16_t blk[16]);
+void oracle_quantize(int16_t blk[16], int dc, int ac);
+int oracle_pick_mb_mode(const uint8_t *target, int ts, uint8_t *p, int stride, int n, int r, int c, uint32_t err[4]);
+int oracle_pick_chroma_mode(const uint8_t *tu, const uint8_t *tv, int ts, uint8_t *pu, uint8_t *pv, int stride, int r, int c);
+int oracle_pick_sub_mode(const int above[8], const int left[4], int p, const uint8_t target[16], uint32_t err[10]);
+int oracle_encode_key_frame(const uint8_t *sy, const uint8_t *su, const uint8_t *sv, int cols, int rows, const int16_t dq[6],
+                            int lf_level, vp8r_mb_info *mbs, int16_t *payload, uint8_t *ry, uint8_t *ru, uint8_t *rv);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,7 +17,7 @@ class FrameHdr(C.Structure):
                 ("filter_type", C.c_uint8), ("loop_filter_level", C.c_uint8), ("sharpness_level", C.c_uint8),
                 ("refresh_last", C.c_uint8), ("refresh_golden", C.c_uint8), ("refresh_altref", C.c_uint8),
                 ("copy_to_golden", C.c_uint8), ("copy_to_altref", C.c_uint8),
-                ("sign_bias_golden", C.c_uint8), ("sign_bias_altref", C.c_uint8), ("reserved0", C.c_uint8 * 1),
+                ("sign_bias_golden", C.c_uint8), ("sign_bias_altref", C.c_uint8), ("q_index", C.c_uint8),
                 ("modes_deferred", C.c_uint8), ("tokens_deferred", C.c_uint8),
                 ("dq", (C.c_int16 * 6) * 4),
                 ("n_coef_blocks", C.c_uint32), ("n_payload_blocks", C.c_uint32),
@@ -71,6 +71,9 @@ SIGNATURES = {
     "vp8r_read_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                   C.POINTER(C.c_size_t), C.c_int]),
     "vp8r_read_batch_packed": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_int]),
+    "vp8r_encode_key_frames": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "vp8r_frame_write_bitstream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "vp8r_read_batch_packed_as": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
     "vp8r_stream_read_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "vp8r_stream_checksum": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),

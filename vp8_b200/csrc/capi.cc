@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "host/frame_parser.h"
+#include "host/frame_writer.h"
 #include "host/parsed_frame.h"
 #include "rt/error.h"
 #include "vp8r.h"
@@ -150,6 +151,24 @@ VP8R_API int vp8r_parse_batch(int n, vp8r_parser *const *parsers, const uint8_t 
     for (auto &e : errs)
       if (!e.empty()) vp8r::SetError(e);
   return first_err.load();
+}
+
+VP8R_API int vp8r_frame_write_bitstream(const vp8r_frame *f, uint8_t *dst, size_t cap, size_t *size) {
+  if (!f || !size) return VP8R_ERR_INVALID_ARG;
+  std::vector<uint8_t> bytes;
+  std::string err;
+  const int rc = vp8r::WriteKeyFrame(*f, &bytes, &err);
+  if (rc != VP8R_OK) {
+    vp8r::SetError(err);
+    return rc;
+  }
+  *size = bytes.size();
+  if (!dst || cap < bytes.size()) {
+    vp8r::SetError("vp8r_frame_write_bitstream: destination too small");
+    return VP8R_ERR_INVALID_ARG;
+  }
+  std::memcpy(dst, bytes.data(), bytes.size());
+  return VP8R_OK;
 }
 
 VP8R_API int vp8r_is_key_frame(const uint8_t *data, size_t size) {

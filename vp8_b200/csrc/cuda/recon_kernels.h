@@ -77,6 +77,10 @@ struct DevFrameJob {
   uint8_t *segment_map;
   uint32_t *level_table;
   DevFrameDyn *dyn;
+  // encoder (K_encode, enc_kernels.cu): macroblock-aligned source planes in device memory; `mbs` and `payload` are
+  // then OUTPUTS (25 coefficient blocks reserved per macroblock)
+  const uint8_t *enc_src[3];
+  int enc_src_pitch_y, enc_src_pitch_c;
 };
 
 // A frame whose device-side parse ran past the end of a partition: its records are not trustworthy, so no
@@ -110,6 +114,9 @@ cudaError_t LaunchInter(const DevFrameJob *jobs, int n_frames, int max_mbs, cuda
 cudaError_t LaunchIntra(const DevFrameJob *jobs, int n_frames, int max_rows, cudaStream_t st);
 // Flat intra: every intra MB of dependency level `level` (frames with n_intra_levels > 0).
 cudaError_t LaunchIntraFlat(const DevFrameJob *jobs, int n_frames, int level, int max_count, cudaStream_t st);
+// K_encode: closed-loop key-frame encoder (mode decision, forward transform, quantisation, reconstruction) of every
+// job with enc_src set; the loop filter follows as for a decoded frame.
+cudaError_t LaunchEncodeIntra(const DevFrameJob *jobs, int n_frames, int max_rows, cudaStream_t st);
 // Up to eight frames with the same geometry and filter type (and a non-zero frame filter level) that one
 // warp of the batch loop filter walks together; unused slots are -1, slot 0 is always used.
 struct FilterGroup {

@@ -89,6 +89,15 @@ void BuildDequant(int q, const int delta[5], int16_t out[6]) {
   out[VP8R_DQ_UV_AC] = int16_t(kAcQ[ClampQ(q + delta[4])]);
 }
 
+}  // namespace
+
+void DequantFactorsForIndex(int q_index, int16_t out[6]) {
+  const int zero[5] = {0, 0, 0, 0, 0};
+  BuildDequant(ClampQ(q_index), zero, out);
+}
+
+namespace {
+
 inline int ReadSigned(BoolReader &br, int bits) {  // magnitude then sign
   int v = int(br.Literal(bits));
   return br.Bit128() ? -v : v;
@@ -251,7 +260,8 @@ int FrameParser::ParseHeader(const uint8_t *data, size_t size, vp8r_frame *out) 
   sign_bias_[0] = sign_bias_[1] = false;
   sign_bias_[2] = h.sign_bias_golden;
   sign_bias_[3] = h.sign_bias_altref;
-  h.reserved0[0] = uint8_t(refresh_entropy);  // consumed by Parse()
+  refresh_entropy_ = refresh_entropy;  // consumed by Parse()
+  h.q_index = uint8_t(y_ac_qi_);
 
   return VP8R_OK;
 }
@@ -772,8 +782,7 @@ int FrameParser::Parse(const uint8_t *data, size_t size, vp8r_frame *out) {
   int rc = ParseHeader(data, size, out);
   if (rc != VP8R_OK) return rc;
   BoolReader &br = first_;
-  const bool refresh_entropy = out->hdr.reserved0[0] != 0;
-  out->hdr.reserved0[0] = 0;
+  const bool refresh_entropy = refresh_entropy_;
 
   // Probability updates of a frame with refresh_entropy_probs == 0 are dropped at its end
   // (bitstream_parser.cc:116-141,276-284,302-309).

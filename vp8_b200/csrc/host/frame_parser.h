@@ -25,6 +25,10 @@ struct EntropyTables {
   uint8_t uvmode[3];
 };
 
+// Dequantisation (= quantisation) factors of one quantiser index without deltas, in VP8R_DQ_* order
+// (src/quantizer.cc:15-53).  Used by the encoder, which writes frames with one quantiser.
+void DequantFactorsForIndex(int q_index, int16_t out[6]);
+
 class FrameParser {
  public:
   FrameParser() { Reset(); }
@@ -60,6 +64,7 @@ class FrameParser {
     return code;
   }
   void LoadDefaults();
+  bool refresh_entropy_ = true;  // of the frame being parsed (ParseHeader -> Parse)
   int ParseHeader(const uint8_t *data, size_t size, vp8r_frame *out);
   int ParseMacroblocks(vp8r_frame *out);
   void ParseInterMb(int r, int c, int idx, int ref, vp8r_mb_info *mb, vp8r_frame *out, bool *split);

@@ -24,6 +24,16 @@ class ParsedFrame:
         check(self._lib.vp8r_frame_get_desc(self.handle, C.byref(d)))
         return d
 
+    def write_bitstream(self):
+        """The frame as a VP8 key frame (the inverse of Parser.parse for what the encoder produces)."""
+        size = C.c_size_t(0)
+        rc = self._lib.vp8r_frame_write_bitstream(self.handle, None, 0, C.byref(size))
+        if size.value == 0:
+            check(rc)
+        buf = (C.c_uint8 * size.value)()
+        check(self._lib.vp8r_frame_write_bitstream(self.handle, buf, size.value, C.byref(size)))
+        return bytes(buf[:size.value])
+
     def close(self):
         if self.handle:
             self._lib.vp8r_frame_destroy(self.handle)
@@ -90,6 +100,24 @@ class Engine:
         sa = (C.c_void_p * n)(*[s.handle for s in streams])
         fa = (C.c_void_p * n)(*[f.handle for f in frames])
         check(self._lib.vp8r_reconstruct_batch(self.handle, n, sa, fa))
+
+    def encode_key_frames(self, streams, images, width, height, q_index, loop_filter_level=0, sharpness=0):
+        """Row f4: one key frame per stream from cropped I420 images (bytes), encoded in a closed loop on the device.
+        Returns the ParsedFrame objects (macroblock records + coefficient blocks; .write_bitstream() serialises them);
+        every stream then holds the reconstructed frame a decoder would produce."""
+        n = len(streams)
+        need = width * height + 2 * ((width + 1) // 2) * ((height + 1) // 2)
+        bufs = []
+        for img in images:
+            if len(img) != need:
+                raise ValueError("image is not a cropped I420 frame of the given size")
+            bufs.append((C.c_uint8 * need).from_buffer_copy(img))
+        frames = [ParsedFrame(pinned=False) for _ in range(n)]
+        sa = (C.c_void_p * n)(*[s.handle for s in streams])
+        ia = (C.c_void_p * n)(*[C.cast(b, C.c_void_p) for b in bufs])
+        fa = (C.c_void_p * n)(*[f.handle for f in frames])
+        check(self._lib.vp8r_encode_key_frames(self.handle, n, sa, ia, width, height, q_index, loop_filter_level, sharpness, fa))
+        return frames
 
     def upload(self, frame, release_host=False):
         """Copies the frame's arrays to HBM; release_host frees the host copy afterwards."""
