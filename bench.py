@@ -509,9 +509,12 @@ def main():
     e2e_dec.decode(payloads, out_packed=packed)  # warm-up (allocations, pinned buffers growth)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
+    for k in range(args.e2e_steps):
+        # one set of S streams after another, as a server would be handed them: the next pass starts while the last
+        # time steps of this one are still on their way (parse -> reconstruction -> read-back is ~100 ms deep);
+        # the last pass drains, and the clock stops after that
         e2e_dec.reset()
-        decoded, shown, h2d, d2h = e2e_dec.decode(payloads, out_packed=packed)
+        decoded, shown, h2d, d2h = e2e_dec.decode(payloads, out_packed=packed, drain=k + 1 == args.e2e_steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     host_seconds = {k: round(v, 3) for k, v in getattr(e2e_dec, "host_seconds", {}).items()}  # last pass, this rank

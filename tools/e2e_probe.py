@@ -31,11 +31,13 @@ for mode in MODES:
         dec.decode(payloads, out_packed=packed if rb else None)
         torch.cuda.synchronize()
         eng.timers(reset=True)
+        PASSES = int(os.environ.get("PROBE_PASSES", "1"))  # > 1: passes follow each other without draining
         t0 = time.perf_counter()
-        dec.reset()
-        dec.decode(payloads, out_packed=packed if rb else None)
+        for k in range(PASSES):
+            dec.reset()
+            dec.decode(payloads, out_packed=packed if rb else None, drain=k + 1 == PASSES)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        dt = (time.perf_counter() - t0) / PASSES
         tm = eng.timers(reset=True)
         print(f"{mode:7s} readback={rb!s:5s} {S*30/dt:8.0f} fps  wall {dt*1e3:7.0f} ms  tokens {tm.ms_tokens:6.0f} recon {tm.ms_inter+tm.ms_intra+tm.ms_filter:6.0f} h2d {tm.ms_h2d:5.0f} pack {tm.ms_d2h:5.0f}", flush=True)
         print("        host seconds:", {k: round(v, 3) for k, v in dec.host_seconds.items()}, flush=True)

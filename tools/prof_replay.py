@@ -30,6 +30,9 @@ def main():
     ap.add_argument("--synth-args", default=ARGS)
     ap.add_argument("--engines", type=int, default=1, help="split the streams over this many engines (own CUDA streams), "
                     "time steps submitted round-robin: kernels of different engines overlap")
+    ap.add_argument("--parse", default="host", choices=["host", "tokens", "device"],
+                    help="what the replay includes: host = reconstruction kernels only; tokens = + the DCT token kernel; "
+                         "device = + the macroblock-header kernel (everything behind the frame headers on the GPU)")
     a = ap.parse_args()
     w, h = (int(x) for x in a.size.split("x"))
     tmp = tempfile.mkdtemp()
@@ -46,7 +49,7 @@ def main():
         return multi_engine(a, payloads)
     eng = vp8_b200.Engine(0)
     eng.set_timing(True)
-    dec = vp8_b200.BatchDecoder(eng, a.streams, pinned=False)
+    dec = vp8_b200.BatchDecoder(eng, a.streams, pinned=False, tokens_on_device=a.parse == "tokens", device_parse=a.parse == "device")
     resident = []
     for t in range(a.frames):
         frames = dec.parse_into([vp8_b200.ParsedFrame(pinned=False) for _ in range(a.streams)], [p[t] for p in payloads],
@@ -70,7 +73,7 @@ def main():
             eng.reconstruct_batch(dec.streams, resident[t])
         tm = eng.timers(reset=True)
         out = {"streams": a.streams, "frames": a.frames, "size": a.size, "ms_inter": tm.ms_inter, "ms_intra": tm.ms_intra,
-               "ms_filter": tm.ms_filter, "filter_ms_per_launch": tm.ms_filter / max(1, tm.launches_filter),
+               "ms_filter": tm.ms_filter, "ms_parse_kernels": tm.ms_tokens, "parse": a.parse, "filter_ms_per_launch": tm.ms_filter / max(1, tm.launches_filter),
                "inter_ms_per_launch": tm.ms_inter / max(1, tm.launches_inter),
                "frames_per_s": tm.frames / max(1e-9, (tm.ms_inter + tm.ms_intra + tm.ms_filter) / 1e3),
                "filter_mode": os.environ.get("VP8R_FILTER", "auto"), "wall_ms_untimed_pass": wall * 1e3,

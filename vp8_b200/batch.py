@@ -18,7 +18,7 @@ class BatchDecoder:
     def __init__(self, engine, n_streams, parse_threads=None, pinned=True, tokens_on_device=False, device_parse=False,
                  depth=2):
         """depth: time steps in flight (parsed-frame slots; out_ring / out_packed passed to decode()
-        must hold as many buffers).  The engine supports up to 4."""
+        must hold as many buffers).  The engine supports up to 8."""
         self.engine = engine
         self._lib = engine._lib
         self.n = n_streams
@@ -41,7 +41,9 @@ class BatchDecoder:
                 else:
                     p.set_defer_tokens(True)
         self.streams = [engine.open_stream() for _ in range(n_streams)]
-        self.depth = max(2, min(4, depth))
+        self.depth = max(2, min(8, depth))
+        self._g = 0          # time steps submitted so far, over all decode() calls: slot / ring entry = step % depth
+        self._tickets = {}   # step -> fence ticket of its kernels and read-back
         self.slots = [[ParsedFrame(pinned=pinned) for _ in range(n_streams)] for _ in range(self.depth)]
 
     def reset(self):
@@ -93,7 +95,7 @@ class BatchDecoder:
     def wait(self, ticket):
         check(self._lib.vp8r_engine_wait(self.engine.handle, ticket))
 
-    def decode(self, payloads, out_ring=None, on_step=None, out_packed=None, shown_only=True):
+    def decode(self, payloads, out_ring=None, on_step=None, out_packed=None, shown_only=True, drain=True):
         """payloads[s] = list of compressed frames of stream s.  out_ring: optional list of `depth` lists
         of (ptr, capacity) pinned host buffers, one per stream, that receive the frames of a time step
         (ring of `depth` steps).  out_packed: optional ((ptr0, ptr1, ...), stride): `depth` pinned host
@@ -101,18 +103,26 @@ class BatchDecoder:
         frame k of the step's live streams at ptr + k*stride.  shown_only (default): only frames with
         show_frame set are read back (the reference never writes a hidden frame, src/decode.cc:76), so frame k
         of the packed buffer is the k-th SHOWN frame of the step.  on_step(t, live, frames) is called after
-        step t has been submitted.
+        step t has been submitted.  drain=False returns without waiting for the last steps: the next decode()
+        (new streams after reset(), same rings) then starts while they finish, as a server that is handed one set
+        of streams after another would run; the ring entry of a step is (steps since the last drain) % depth, and the
+        last call has to drain (or the caller calls engine.sync()).
         Returns (frames decoded, frames shown, h2d bytes, d2h bytes)."""
         steps = max(len(p) for p in payloads)
         decoded = shown = h2d = d2h = 0
         self.host_seconds = {"parse": 0.0, "submit": 0.0, "readback": 0.0, "wait": 0.0, "account": 0.0}
         hs, clock = self.host_seconds, time.perf_counter
-        tickets = {}
+        tickets, g0, depth = self._tickets, self._g, self.depth
         live = [i for i in range(self.n) if len(payloads[i]) > 0]
         t0 = clock()
-        frames = self.parse_step(0, [p[0] if p else b"" for p in payloads], live)
+        if g0 - depth in tickets:
+            self.wait(tickets.pop(g0 - depth))
+        hs["wait"] += clock() - t0
+        t0 = clock()
+        frames = self.parse_step(g0 % depth, [p[0] if p else b"" for p in payloads], live)
         hs["parse"] += clock() - t0
         for t in range(steps):
+            g = g0 + t
             t0 = clock()
             streams = [self.streams[i] for i in live]
             self.engine.reconstruct_batch(streams, frames)
@@ -129,29 +139,33 @@ class BatchDecoder:
             hs["account"] += clock() - t0
             t0 = clock()
             if out_ring is not None and out_idx:
-                ring = out_ring[t % self.depth]
+                ring = out_ring[g % depth]
                 self.engine.read_batch([streams[k] for k in out_idx], [ring[live[k]][0] for k in out_idx],
                                        [ring[live[k]][1] for k in out_idx], async_=True)
                 d2h += sum(streams[k].frame_bytes() for k in out_idx)
             if out_packed is not None and out_idx:
                 (ptrs, stride) = out_packed
-                self.engine.read_batch_packed([streams[k] for k in out_idx], ptrs[t % self.depth], stride, async_=True)
+                self.engine.read_batch_packed([streams[k] for k in out_idx], ptrs[g % depth], stride, async_=True)
                 d2h += len(out_idx) * stride
-            tickets[t] = self.fence()
+            tickets[g] = self.fence()
             hs["readback"] += clock() - t0
             if on_step:
                 on_step(t, live, frames)
             if t + 1 < steps:
-                old = t + 1 - self.depth
+                old = g + 1 - depth
                 t0 = clock()
                 if old in tickets:
-                    self.wait(tickets.pop(old))  # slot and ring entry (t+1) % depth are free again
+                    self.wait(tickets.pop(old))  # slot and ring entry (g+1) % depth are free again
                 hs["wait"] += clock() - t0
                 t0 = clock()
                 live = [i for i in range(self.n) if len(payloads[i]) > t + 1]
-                frames = self.parse_step((t + 1) % self.depth, [p[t + 1] if len(p) > t + 1 else b"" for p in payloads], live)
+                frames = self.parse_step((g + 1) % depth, [p[t + 1] if len(p) > t + 1 else b"" for p in payloads], live)
                 hs["parse"] += clock() - t0
-        self.engine.sync()
+        self._g = g0 + steps
+        if drain:
+            self.engine.sync()
+            tickets.clear()
+            self._g = 0
         return decoded, shown, h2d, d2h
 
     def close(self):

@@ -96,10 +96,14 @@ __device__ __forceinline__ const uint32_t *JobLevelTable(const DevFrameJob &j) {
 // Uploads the constant tables (filter taps, B_PRED gather LUT).  Once per device.
 cudaError_t InitKernelTables();
 
-// K_tokens: device-side token decode of every job with tok_hdr != nullptr (see token_kernel.cu).
-// `modes`: some job also has mode_hdr (one more working thread per frame, more shared memory).
-cudaError_t LaunchTokens(const DevFrameJob *jobs, int n_frames, int max_cols, int max_mbs, int max_parts, bool modes,
-                         cudaStream_t st);
+// Device-side parse (token_kernel.cu).  K_modes: macroblock headers of every job with mode_hdr != nullptr, one
+// single-lane warp per frame; independent of every other frame, so the launches of consecutive batches may run
+// concurrently.  K_segments: persistent segment maps + the segment-dependent record fields of those jobs; has to
+// run in batch order, after K_modes and before K_tokens of its batch.  K_tokens: DCT token partitions of every
+// job with tok_hdr != nullptr.
+cudaError_t LaunchModes(const DevFrameJob *jobs, int n_frames, int max_cols, int max_mbs, cudaStream_t st);
+cudaError_t LaunchSegments(const DevFrameJob *jobs, int n_frames, int max_mbs, cudaStream_t st);
+cudaError_t LaunchTokens(const DevFrameJob *jobs, int n_frames, int max_cols, int max_parts, cudaStream_t st);
 cudaError_t InitParseTables();
 // Level-scheduled intra prediction of frames whose level table was built on the device: one CTA per
 // frame walks the dependency levels with a block barrier in between.

@@ -17,14 +17,22 @@
 // coefficient area, row r compact inside its own region starting at block r * cols * 25;
 // coef_mask / coef_offset / VP8R_MB_LF_INNER of every vp8r_mb_info are completed in place.
 //
-// Deferred modes (vp8r_frame_hdr.modes_deferred): one more warp per CTA reads the per-macroblock
-// syntax of the first partition (segment id, skip flag, intra modes incl. the 16 B_PRED sub-modes,
-// reference frame, the near/nearest/best motion-vector search, NEW and SPLIT vectors) in raster
-// order, writes the vp8r_mb_info records the reconstruction kernels consume, computes the loop-filter
-// level of every macroblock and the intra dependency levels of inter frames.  The token threads
-// follow it through a shared progress counter.  Replaces ParseMacroblocks / ParseInterMb /
+// Deferred modes (vp8r_frame_hdr.modes_deferred): K_modes, a kernel of its own with one single-lane warp per
+// frame, reads the per-macroblock syntax of the first partition (segment id, skip flag, intra modes incl. the 16
+// B_PRED sub-modes, reference frame, the near/nearest/best motion-vector search, NEW and SPLIT vectors) in raster
+// order, writes the vp8r_mb_info records the reconstruction kernels consume, computes the loop-filter level of
+// every macroblock and the intra dependency levels of inter frames.  Replaces ParseMacroblocks / ParseInterMb /
 // BuildIntraLevels of host/frame_parser.cc, i.e. src/bitstream_parser.cc:320-464,539-568,
 // src/inter_predict.cc:8-244, src/intra_predict.cc:176-183 of the reference.
+//
+// A header chain is the longest serial chain of a frame (~29 ms for 1080p against ~12 ms for a token partition)
+// and needs nothing of the frame before it EXCEPT the persistent segment map.  So the map is taken out of the
+// chain: K_modes never touches it, and K_segments, a one-thread-per-macroblock kernel the engine runs in batch
+// order, stores the ids of frames that code a map and patches segment / loop-filter level into the records of
+// frames that inherit it.  That leaves the header kernels of consecutive time steps free to run side by side
+// (one engine stream per batch slot), which is where the parse throughput comes from: a 32-thread CTA with
+// ~14 KB of shared memory lets sixteen chains share an SM instead of five frame-CTAs that each wait for their
+// slowest chain.
 #include <cstdlib>
 
 #include "recon_kernels.h"
@@ -195,8 +203,6 @@ struct TokenShared {
   unsigned char probs[4 * 8 * 3 * 11];
   int progress[8];      // progress[w]: macroblocks finished by partition w, counted along its rows
   short blk[8][16];     // staging of the block being decoded, one per warp
-  int modes_done;       // macroblocks (raster) whose vp8r_mb_info the mode thread has written
-  int pad[3];
 };
 
 // Tokens of one block whose first symbol was not end-of-block (src/bitstream_parser.cc:572-621).
@@ -249,23 +255,29 @@ __device__ __forceinline__ int ReadTokens(BoolDec &bd, const unsigned char *prob
 
 }  // namespace
 
-constexpr int kTokenWarps = 8;           // token partitions; the mode thread is warp kTokenWarps
+constexpr int kTokenWarps = 8;           // token partitions
 constexpr int kMaxFlatLevels = 48;       // as FrameParser::kMaxFlatIntraLevels
 constexpr int kMaxLevelMbs = 96 * 1024;  // frames with more macroblocks use the intra wavefront kernel
 
-struct SmemLayout {
-  size_t tabs, above, mbctx, above_sub, above_bmodes, levels, cnt, total;
+// Shared memory of K_tokens: TokenShared, then the above-context of every macroblock column.
+__host__ __device__ inline size_t TokenSmem(int cols) {
+  return ((sizeof(TokenShared) + 15) & ~size_t(15)) + ((size_t(cols) * 2 + 15) & ~size_t(15));
+}
+// Shared memory of K_modes.
+struct ModeLayout {
+  size_t tabs, fp, sub, mbctx, above_sub, above_bmodes, levels, cnt, total;
 };
-__host__ __device__ inline SmemLayout MakeLayout(int cols, int n_mb, bool modes) {
-  SmemLayout l;
-  size_t at = (sizeof(TokenShared) + 15) & ~size_t(15);
-  l.above = at; at += (size_t(cols) * 2 + 15) & ~size_t(15);
-  l.tabs = at; if (modes) at += (sizeof(ModeTables) + 15) & ~size_t(15);
-  l.mbctx = at; if (modes) at += size_t(cols) * 2 * 8;
-  l.above_sub = at; if (modes) at += size_t(cols) * 16;
-  l.above_bmodes = at; if (modes) at += (size_t(cols) * 4 + 15) & ~size_t(15);
-  l.cnt = at; if (modes) at += (kMaxFlatLevels + 2) * 4;
-  l.levels = at; if (modes) at += (size_t(n_mb <= kMaxLevelMbs ? n_mb : 0) + 15) & ~size_t(15);
+__host__ __device__ inline ModeLayout MakeModeLayout(int cols, int n_mb) {
+  ModeLayout l;
+  size_t at = 0;
+  l.tabs = at; at += (sizeof(ModeTables) + 15) & ~size_t(15);
+  l.fp = at; at += 64;
+  l.sub = at; at += 64;
+  l.mbctx = at; at += size_t(cols) * 2 * 8;
+  l.above_sub = at; at += size_t(cols) * 16;
+  l.above_bmodes = at; at += (size_t(cols) * 4 + 15) & ~size_t(15);
+  l.cnt = at; at += ((kMaxFlatLevels + 2) * 4 + 15) & ~size_t(15);
+  l.levels = at; at += (size_t(n_mb <= kMaxLevelMbs ? n_mb : 0) + 15) & ~size_t(15);
   l.total = at;
   return l;
 }
@@ -288,11 +300,28 @@ __device__ __forceinline__ int ReadMvComponent(BoolDec &bd, const unsigned char 
   return (int)(short)a;
 }
 
+// Loop-filter level of a macroblock (src/bitstream_parser.cc:539-568).  mode_delta: the mode_lf_delta entry that
+// applies (B_PRED: [0], ZERO: [1], SPLIT: [3], other inter modes: [2]; 0 for the other intra modes).
+__device__ __forceinline__ int MbFilterLevel(int frame_lf, bool seg_enabled, bool seg_abs, int seg_lf, bool lf_adj,
+                                             int ref_delta, int ref, int mode_delta) {
+  int lvl = frame_lf;
+  if (seg_enabled) {
+    lvl = seg_abs ? seg_lf : lvl + seg_lf;
+    lvl = lvl < 0 ? 0 : (lvl > 63 ? 63 : lvl);
+  }
+  if (lf_adj) {
+    lvl += ref_delta + mode_delta;
+    (void)ref;
+    lvl = lvl < 0 ? 0 : (lvl > 63 ? 63 : lvl);
+  }
+  return lvl;
+}
+
 // The macroblock-header pass of one frame by one thread (see the file comment).
-__device__ void ModeThread(const DevFrameJob &job, const vp8r_token_hdr *th, unsigned char *smem, TokenShared &sh) {
+__device__ void ModeThread(const DevFrameJob &job, const vp8r_token_hdr *th, unsigned char *smem) {
   const vp8r_mode_hdr *mhp = reinterpret_cast<const vp8r_mode_hdr *>(job.mode_hdr);
   const int cols = job.mb_cols, rows = job.mb_rows, n_mb = cols * rows;
-  const SmemLayout lay = MakeLayout(cols, n_mb, true);
+  const ModeLayout lay = MakeModeLayout(cols, n_mb);
   const ModeTables &T = *reinterpret_cast<const ModeTables *>(smem + lay.tabs);
   uint2 *mbctx = reinterpret_cast<uint2 *>(smem + lay.mbctx);        // [2][cols]: x = 1 | ref<<1 | mode<<3 (0: intra), y = mv
   int *above_sub = reinterpret_cast<int *>(smem + lay.above_sub);      // [cols][4]: bottom-row sub-block MVs of the MB above
@@ -308,9 +337,8 @@ __device__ void ModeThread(const DevFrameJob &job, const vp8r_token_hdr *th, uns
   const int frame_lf = mhp->frame_lf_level;
   unsigned sign_bias = 0;
   for (int i = 0; i < 4; ++i) sign_bias |= (unsigned)(mhp->sign_bias[i] != 0) << i;
-  // small per-frame probability sets live in shared memory behind the token probabilities' CTA copy
-  __shared__ int sub[16];           // sub-block motion vectors of the current SPLIT macroblock
-  __shared__ unsigned char fp[64];  // [0..3] ymode, [4..6] uvmode, [8..10] segment tree, [16..53] mv
+  int *sub = reinterpret_cast<int *>(smem + lay.sub);  // sub-block motion vectors of the current SPLIT macroblock
+  unsigned char *fp = smem + lay.fp;                   // [0..3] ymode, [4..6] uvmode, [8..10] segment tree, [16..53] mv
   for (int i = 0; i < 4; ++i) fp[i] = mhp->ymode_probs[i];
   for (int i = 0; i < 3; ++i) fp[4 + i] = mhp->uvmode_probs[i], fp[8 + i] = mhp->segment_tree_probs[i];
   for (int i = 0; i < 38; ++i) fp[16 + i] = (&mhp->mv_probs[0][0])[i];
@@ -323,8 +351,6 @@ __device__ void ModeThread(const DevFrameJob &job, const vp8r_token_hdr *th, uns
 
   vp8r_mb_info *mbs = const_cast<vp8r_mb_info *>(job.mbs);
   int16_t *payload = const_cast<int16_t *>(job.payload);
-  unsigned char *segmap = job.segment_map;
-  volatile int *done = &sh.modes_done;
   unsigned n_inter = 0, n_split = 0, max_level = 0;
   bool level_overflow = !have_levels;
 
@@ -337,24 +363,13 @@ __device__ void ModeThread(const DevFrameJob &job, const vp8r_token_hdr *th, uns
     unsigned left_level = 0, aboveleft_level = 0;
     const int to_top = -(r * 16) * 8, to_bottom = ((rows - 1 - r) * 16) * 8;
 
-    const bool read_map = !update_map && !key;
-    unsigned seg_next = read_map ? segmap[r * cols] : 0u;  // fetched one macroblock ahead
     for (int c = 0; c < cols; ++c) {
       const int idx = r * cols + c;
       const uint2 above_ctx = r > 0 ? ctx_abv[c] : make_uint2(0, 0);
-      const unsigned seg_cur = seg_next;
-      if (read_map && c + 1 < cols) seg_next = segmap[idx + 1];
       // --- pre-header (src/bitstream_parser.cc:320-352) ---
-      int seg;
-      if (update_map) {
-        seg = bd.Tree(T.tree_segment, fp + 8);
-        segmap[idx] = (unsigned char)seg;
-      } else if (key) {
-        seg = 0;  // a key frame rebuilds the parser context: the persistent map starts from zero
-        segmap[idx] = 0;
-      } else {
-        seg = (int)seg_cur;
-      }
+      // Without a coded map the id is inherited from the persistent map: K_segments fills it in (and the level
+      // that hangs on it) after this kernel; nothing else of the syntax depends on it.
+      const int seg = update_map ? bd.Tree(T.tree_segment, fp + 8) : 0;
       const int skip = no_skip ? bd.Bit(prob_skip) : 0;
       const int is_inter = key ? 0 : bd.Bit(prob_intra);
 
@@ -503,24 +518,9 @@ __device__ void ModeThread(const DevFrameJob &job, const vp8r_token_hdr *th, uns
       // --- loop-filter level (src/bitstream_parser.cc:539-568), flags ---
       const bool has_y2 = is_inter ? !split : !bpred;
       const int qseg = seg_enabled ? seg : 0;
-      int lvl = frame_lf;
-      if (seg_enabled) {
-        lvl = seg_abs ? seg_lf[seg] : lvl + seg_lf[seg];
-        lvl = lvl < 0 ? 0 : (lvl > 63 ? 63 : lvl);
-      }
-      if (lf_adj) {
-        lvl += ref_delta[ref];
-        if (ref == 0) {
-          if (bpred) lvl += mode_delta[0];
-        } else if (inter_mode == MV_ZERO) {
-          lvl += mode_delta[1];
-        } else if (inter_mode == MV_SPLIT) {
-          lvl += mode_delta[3];
-        } else {
-          lvl += mode_delta[2];
-        }
-        lvl = lvl < 0 ? 0 : (lvl > 63 ? 63 : lvl);
-      }
+      const int lvl = MbFilterLevel(frame_lf, seg_enabled, seg_abs, seg_lf[seg], lf_adj, ref_delta[ref], ref,
+                                    ref == 0 ? (bpred ? mode_delta[0] : 0)
+                                             : mode_delta[inter_mode == MV_ZERO ? 1 : (inter_mode == MV_SPLIT ? 3 : 2)]);
       flags |= (has_y2 ? VP8R_MB_HAS_Y2 : 0u) | ((unsigned)qseg << VP8R_MB_QSEG_SHIFT) | ((unsigned)lvl << VP8R_MB_LF_SHIFT) |
                ((bpred || split) ? VP8R_MB_LF_INNER : 0u) | (skip ? VP8R_MB_SKIP_COEF : 0u);
 
@@ -565,13 +565,6 @@ __device__ void ModeThread(const DevFrameJob &job, const vp8r_token_hdr *th, uns
           for (int k = 0; k < 4; ++k) above_sub[c * 4 + k] = mbmv, left_sub[k] = mbmv;
         }
       }
-#ifndef VP8R_MODE_PUBLISH
-#define VP8R_MODE_PUBLISH 4
-#endif
-      if ((idx & (VP8R_MODE_PUBLISH - 1)) == VP8R_MODE_PUBLISH - 1 || idx + 1 == n_mb) {  // the token threads follow a few macroblocks behind
-        __threadfence_block();
-        *done = idx + 1;
-      }
     }
   }
 
@@ -606,45 +599,77 @@ __device__ void ModeThread(const DevFrameJob &job, const vp8r_token_hdr *th, uns
   }
 }
 
-// Block = (most DCT partitions of any frame in the batch + 1) warps; the mode thread is the last warp.
-// Only one lane per warp works, but registers are allocated for all 32: the trimmed block keeps a
-// batch's footprint small enough to share the SMs with the reconstruction kernels of the previous
-// time step.  (A register cap was tried: spills in the serial chain cost more than the occupancy won.)
-// kBlockWarps / kMinBlocks: launch bounds.  Frames with up to four DCT partitions run in 160-thread blocks that
-// may be capped to 56 registers (seven frames per SM instead of five): that only pays when more frames are in
-// flight than five per SM hold (VP8R_TOKEN_MINBLOCKS, measured in profiles/r2_summary.md).
+// K_modes: one 32-thread CTA per frame with deferred modes; lane 0 walks the first partition.
+__global__ void __launch_bounds__(32) ModeKernel(const DevFrameJob *__restrict__ jobs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const DevFrameJob &job = jobs[blockIdx.x];
+  if (!job.tok_hdr || !job.mode_hdr) return;
+  const int cols = job.mb_cols, rows = job.mb_rows;
+  const ModeLayout lay = MakeModeLayout(cols, cols * rows);
+  for (int i = threadIdx.x; i < (int)(sizeof(ModeTables) + 3) / 4; i += 32)
+    reinterpret_cast<unsigned *>(smem_raw + lay.tabs)[i] = reinterpret_cast<const unsigned *>(&c_mode_tables)[i];
+  for (int i = threadIdx.x; i < cols * 4; i += 32) smem_raw[lay.above_bmodes + i] = B_DC;
+  for (int i = threadIdx.x; i < kMaxFlatLevels + 2; i += 32) reinterpret_cast<unsigned *>(smem_raw + lay.cnt)[i] = 0;
+  __syncwarp();
+  if (threadIdx.x != 0) return;
+  ModeThread(job, reinterpret_cast<const vp8r_token_hdr *>(job.tok_hdr), smem_raw);
+}
+
+// K_segments: the persistent segment map of every stream, in batch order (see the file comment).  One thread per
+// macroblock.  A frame that codes a map (update_mb_segmentation_map) stores its ids; a key frame without one
+// clears the map (the parser context restarts, host/frame_parser.cc); an inter frame with segmentation but no
+// coded map takes its ids from the map and gets segment and loop-filter level patched into its records.
+__global__ void __launch_bounds__(256) SegmentKernel(const DevFrameJob *__restrict__ jobs) {
+  const DevFrameJob &job = jobs[blockIdx.y];
+  if (!job.mode_hdr || JobFailed(job)) return;
+  const vp8r_mode_hdr *mh = reinterpret_cast<const vp8r_mode_hdr *>(job.mode_hdr);
+  const int n_mb = job.mb_cols * job.mb_rows;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= n_mb) return;
+  unsigned char *segmap = job.segment_map;
+  vp8r_mb_info *mbs = const_cast<vp8r_mb_info *>(job.mbs);
+  if (mh->update_segment_map) {
+    segmap[idx] = (unsigned char)((mbs[idx].flags >> VP8R_MB_QSEG_SHIFT) & 3u);
+  } else if (mh->key_frame) {
+    segmap[idx] = 0;
+  } else if (mh->segmentation_enabled) {
+    const int seg = segmap[idx] & 3;
+    unsigned flags = mbs[idx].flags;
+    const int ref = (int)((flags >> VP8R_MB_REF_SHIFT) & 3u), mode = (int)((flags >> VP8R_MB_MODE_SHIFT) & 7u);
+    const int lvl = MbFilterLevel(mh->frame_lf_level, true, mh->segment_abs != 0, mh->segment_lf[seg], mh->lf_adj_enable != 0,
+                                  mh->ref_lf_delta[ref], ref,
+                                  ref == 0 ? (mode == B_PRED ? mh->mode_lf_delta[0] : 0)
+                                           : mh->mode_lf_delta[mode == MV_ZERO ? 1 : (mode == MV_SPLIT ? 3 : 2)]);
+    flags &= ~((3u << VP8R_MB_QSEG_SHIFT) | (63u << VP8R_MB_LF_SHIFT));
+    flags |= ((unsigned)seg << VP8R_MB_QSEG_SHIFT) | ((unsigned)lvl << VP8R_MB_LF_SHIFT);
+    mbs[idx].flags = flags;
+  }
+}
+
+// K_tokens.  Block = (most DCT partitions of any frame in the batch) warps.  Only one lane per warp works, but
+// registers are allocated for all 32: the trimmed block keeps a batch's footprint small enough to share the SMs
+// with the reconstruction kernels of the previous time step.  (A register cap was tried: spills in the serial
+// chain cost more than the occupancy won.)
+// kBlockWarps / kMinBlocks: launch bounds (VP8R_TOKEN_MINBLOCKS, measured in profiles/r2_summary.md).
 template <int kBlockWarps, int kMinBlocks>
 __global__ void __launch_bounds__(kBlockWarps * 32, kMinBlocks) TokenKernel(const DevFrameJob *__restrict__ jobs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const DevFrameJob &job = jobs[blockIdx.x];
   if (!job.tok_hdr) return;
   TokenShared &sh = *reinterpret_cast<TokenShared *>(smem_raw);
-  const bool modes = job.mode_hdr != nullptr;
   const vp8r_token_hdr *th = reinterpret_cast<const vp8r_token_hdr *>(job.tok_hdr);
   const int cols = job.mb_cols, rows = job.mb_rows;
-  const SmemLayout lay = MakeLayout(cols, cols * rows, modes);
   // above-context per macroblock column: bits 0-3 Y (column j), 4-5 U, 6-7 V, 8 Y2
-  unsigned short *above = reinterpret_cast<unsigned short *>(smem_raw + lay.above);
+  unsigned short *above = reinterpret_cast<unsigned short *>(smem_raw + ((sizeof(TokenShared) + 15) & ~size_t(15)));
   for (int i = threadIdx.x; i < (int)sizeof(sh.probs) / 4; i += blockDim.x)
     reinterpret_cast<unsigned *>(sh.probs)[i] = __ldg(reinterpret_cast<const unsigned *>(th->coef_probs) + i);
   for (int i = threadIdx.x; i < cols; i += blockDim.x) above[i] = 0;
   if (threadIdx.x < 8) sh.progress[threadIdx.x] = 0;
-  if (threadIdx.x == 0) sh.modes_done = 0;
   for (int i = threadIdx.x; i < 8 * 16; i += blockDim.x) (&sh.blk[0][0])[i] = 0;
-  if (modes) {
-    for (int i = threadIdx.x; i < (int)(sizeof(ModeTables) + 3) / 4; i += blockDim.x)
-      reinterpret_cast<unsigned *>(smem_raw + lay.tabs)[i] = reinterpret_cast<const unsigned *>(&c_mode_tables)[i];
-    for (int i = threadIdx.x; i < cols * 4; i += blockDim.x) smem_raw[lay.above_bmodes + i] = B_DC;
-    for (int i = threadIdx.x; i < kMaxFlatLevels + 2; i += blockDim.x) reinterpret_cast<unsigned *>(smem_raw + lay.cnt)[i] = 0;
-  }
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane != 0) return;
-  if (warp == (int)(blockDim.x >> 5) - 1) {  // last warp: macroblock headers
-    if (modes) ModeThread(job, th, smem_raw, sh);
-    return;
-  }
   const int n_parts = (int)__ldg(&th->n_parts);
   if (warp >= n_parts) return;
 
@@ -658,8 +683,6 @@ __global__ void __launch_bounds__(kBlockWarps * 32, kMinBlocks) TokenKernel(cons
   vp8r_mb_info *mbs = const_cast<vp8r_mb_info *>(job.mbs);
   short *const blk = sh.blk[warp];
   volatile int *const prog = sh.progress;
-  volatile int *const modes_done = &sh.modes_done;
-  int modes_seen = modes ? 0 : 0x7fffffff;
   const int prev_warp = (warp + n_parts - 1) % n_parts;
   int16_t *const coef_area = const_cast<int16_t *>(job.payload) + (size_t)job.coef_base * 16;
 
@@ -673,13 +696,7 @@ __global__ void __launch_bounds__(kBlockWarps * 32, kMinBlocks) TokenKernel(cons
     const int prev_row_base = (warp ? k : k - 1) * cols;
     for (int c = 0; c < cols; ++c) {
       const size_t idx = (size_t)r * cols + c;
-      if (modes_seen <= (int)idx) {  // the record must have been written by the mode thread
-        // the header thread needs ~2.5 us per macroblock and publishes every 4: poll at that pace, not faster
-        // (the spin was 22 % of the kernel's issued instructions with a 200 ns sleep)
-        while ((modes_seen = *modes_done) <= (int)idx) __nanosleep(1000);
-        __threadfence_block();
-      }
-      const unsigned flags = *reinterpret_cast<volatile const unsigned *>(&mbs[idx].flags);
+      const unsigned flags = mbs[idx].flags;
       if (r > 0 && n_parts > 1) {
         const int need = prev_row_base + c + 1;
         while (prog[prev_warp] < need) __nanosleep(100);
@@ -782,30 +799,47 @@ cudaError_t InitParseTables() {
   return cudaMemcpyToSymbol(c_mode_tables, &t, sizeof(t));
 }
 
-size_t ParseKernelSmem(int max_cols, int max_mbs, bool modes) { return MakeLayout(max_cols, max_mbs, modes).total + 16; }
-
-cudaError_t LaunchTokens(const DevFrameJob *jobs, int n_frames, int max_cols, int max_mbs, int max_parts, bool modes,
-                         cudaStream_t st) {
-  const size_t smem = ParseKernelSmem(max_cols, max_mbs, modes);
-  // the attribute belongs to the (function, device) pair: one high-water mark per device
-  max_parts = max_parts < 1 ? 1 : (max_parts > kTokenWarps ? kTokenWarps : max_parts);
-  static const int min_blocks = [] { const char *v = std::getenv("VP8R_TOKEN_MINBLOCKS"); return v ? std::atoi(v) : 0; }();
-  const int variant = max_parts <= 4 ? (min_blocks >= 8 ? 3 : (min_blocks >= 7 ? 2 : (min_blocks >= 6 ? 1 : 0))) : 0;
-  void (*kernel)(const DevFrameJob *) = variant == 3   ? TokenKernel<5, 8>
-                                         : variant == 2 ? TokenKernel<5, 7>
-                                         : variant == 1 ? TokenKernel<5, 6>
-                                                        : TokenKernel<kTokenWarps + 1, 0>;
-  // the attribute belongs to the (function, device) pair: one high-water mark per device and variant
-  static size_t configured[64][4] = {};
+namespace {
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the (function, device) pair: one high-water mark each.
+template <typename K>
+cudaError_t EnsureSmem(K kernel, size_t smem, size_t *marks) {
   int dev = 0;
   cudaGetDevice(&dev);
-  size_t &mark = configured[dev & 63][variant];
+  size_t &mark = marks[dev & 63];
   if (smem > 48 * 1024 && smem > mark) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     mark = smem;
   }
-  kernel<<<n_frames, (max_parts + 1) * 32, smem, st>>>(jobs);
+  return cudaSuccess;
+}
+}  // namespace
+
+cudaError_t LaunchModes(const DevFrameJob *jobs, int n_frames, int max_cols, int max_mbs, cudaStream_t st) {
+  const size_t smem = MakeModeLayout(max_cols, max_mbs).total;
+  static size_t marks[64] = {};
+  cudaError_t e = EnsureSmem(ModeKernel, smem, marks);
+  if (e != cudaSuccess) return e;
+  ModeKernel<<<n_frames, 32, smem, st>>>(jobs);
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchSegments(const DevFrameJob *jobs, int n_frames, int max_mbs, cudaStream_t st) {
+  SegmentKernel<<<dim3((max_mbs + 255) / 256, n_frames), 256, 0, st>>>(jobs);
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchTokens(const DevFrameJob *jobs, int n_frames, int max_cols, int max_parts, cudaStream_t st) {
+  const size_t smem = TokenSmem(max_cols);
+  max_parts = max_parts < 1 ? 1 : (max_parts > kTokenWarps ? kTokenWarps : max_parts);
+  static const int min_blocks = [] { const char *v = std::getenv("VP8R_TOKEN_MINBLOCKS"); return v ? std::atoi(v) : 0; }();
+  // (min blocks 0 = "unspecified" makes ptxas settle on 48 registers with spills for this kernel; 1 gives 72, none)
+  const int variant = max_parts <= 4 ? (min_blocks >= 8 ? 2 : 1) : 0;
+  void (*kernel)(const DevFrameJob *) = variant == 2 ? TokenKernel<4, 8> : variant == 1 ? TokenKernel<4, 1> : TokenKernel<kTokenWarps, 1>;
+  static size_t marks[3][64] = {};
+  cudaError_t e = EnsureSmem(kernel, smem, marks[variant]);
+  if (e != cudaSuccess) return e;
+  kernel<<<n_frames, max_parts * 32, smem, st>>>(jobs);
   return cudaGetLastError();
 }
 

@@ -89,7 +89,8 @@ struct Slot {
   uint8_t *d_arena = nullptr;
   size_t arena_cap = 0;
   cudaEvent_t done = nullptr;
-  cudaEvent_t parsed = nullptr;  // staging + parse kernel of this slot's batch finished (on st_parse)
+  cudaEvent_t parsed = nullptr;  // staging + parse kernels of this slot's batch finished (on the slot's parse stream)
+  cudaEvent_t modes_done = nullptr, segments_done = nullptr;  // K_modes of the batch (parse stream), K_segments (st_segments)
   bool pending = false;
   // Device-side parse: one error word per job (mapped pinned host memory; bit 0: a DCT partition was read past
   // its end, bit 1: the first partition was) and the streams of the batch, so that a failure names its stream.
@@ -104,8 +105,11 @@ struct vp8r_engine {
   int device = 0;
   cudaStream_t st = nullptr;
   bool own_stream = false;
-  static constexpr int kSlots = 4;     // batches in flight between the host and the last kernel
-  static constexpr int kPackBufs = 4;  // packed read-backs in flight
+  // Batches in flight between the host and the last kernel / packed read-backs in flight.  A batch of
+  // device-parsed frames is ~100 ms on its way (header chains, token chains, reconstruction, read-back), so the
+  // rate is (batches in flight) / latency until something saturates: eight, not four (profiles/r2_summary.md).
+  static constexpr int kSlots = 8;
+  static constexpr int kPackBufs = 8;
   Slot slots[kSlots];
   int cur_slot = 0;
   // ticket + per-(frame, band) progress words of the wavefront kernels
@@ -116,12 +120,15 @@ struct vp8r_engine {
   uint8_t *d_pack = nullptr;
   size_t pack_cap = 0;  // bytes per half
   cudaStream_t st_copy = nullptr;
-  // parse stream: staging + K_tokens of time step t+1 run here while the reconstruction kernels of
-  // step t run on `st` (the parse kernel is a few hundred latency-bound threads; it leaves the SMs'
-  // issue slots to the reconstruction kernels)
-  cudaStream_t st_parse = nullptr;
-  cudaEvent_t pack_done[4] = {}, copy_done[4] = {};
-  bool copy_busy[4] = {false, false, false, false};
+  // parse streams, one per batch slot: staging, K_modes and K_tokens of the time steps in flight run side by
+  // side here while the reconstruction kernels of the oldest run on `st` (the parse kernels are latency-bound
+  // single-lane chains: what they need is many of them resident, and they leave the SMs' issue slots to the
+  // reconstruction kernels).  K_segments, the only cross-frame dependency of the parse, runs on st_segments in
+  // batch order between K_modes and K_tokens of its batch.
+  cudaStream_t st_parse[kSlots] = {};
+  cudaStream_t st_segments = nullptr;
+  cudaEvent_t pack_done[kPackBufs] = {}, copy_done[kPackBufs] = {};
+  bool copy_busy[kPackBufs] = {};
   cudaEvent_t fence_copy_ev[16] = {};
   bool fence_has_copy[16] = {};
   // checksum scratch
@@ -154,6 +161,15 @@ namespace {
 int EnsureDevice(vp8r_engine *e) {
   CU_TRY(cudaSetDevice(e->device));
   return VP8R_OK;
+}
+
+cudaError_t SyncParseStreams(vp8r_engine *e) {
+  for (auto st : e->st_parse)
+    if (st) {
+      cudaError_t err = cudaStreamSynchronize(st);
+      if (err != cudaSuccess) return err;
+    }
+  return e->st_segments ? cudaStreamSynchronize(e->st_segments) : cudaSuccess;
 }
 
 void FreeSurfaces(vp8r_stream *s) {
@@ -254,7 +270,7 @@ int ConfigureStream(vp8r_stream *s, const vp8r_frame_hdr &h) {
     s->height = h.height;
     return VP8R_OK;
   }
-  CU_TRY(cudaStreamSynchronize(s->eng->st_parse));
+  CU_TRY(SyncParseStreams(s->eng));
   CU_TRY(cudaStreamSynchronize(s->eng->st));
   FreeSurfaces(s);
   const int B = vp8r::kBorder;
@@ -513,9 +529,12 @@ VP8R_API int vp8r_engine_create(int device, void *cuda_stream, vp8r_engine **out
   for (auto &sl : e->slots) {
     cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&sl.parsed, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&sl.modes_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&sl.segments_done, cudaEventDisableTiming);
   }
   cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&e->st_parse, cudaStreamNonBlocking);
+  for (auto &st : e->st_parse) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&e->st_segments, cudaStreamNonBlocking);
   for (int k = 0; k < vp8r_engine::kPackBufs; ++k) {
     cudaEventCreateWithFlags(&e->pack_done[k], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->copy_done[k], cudaEventDisableTiming);
@@ -539,10 +558,10 @@ VP8R_API void vp8r_engine_destroy(vp8r_engine *e) {
     cudaStreamSynchronize(e->st_copy);
     cudaStreamDestroy(e->st_copy);
   }
-  if (e->st_parse) {
-    cudaStreamSynchronize(e->st_parse);
-    cudaStreamDestroy(e->st_parse);
-  }
+  SyncParseStreams(e);
+  for (auto &st : e->st_parse)
+    if (st) cudaStreamDestroy(st);
+  if (e->st_segments) cudaStreamDestroy(e->st_segments);
   for (int k = 0; k < vp8r_engine::kPackBufs; ++k) {
     if (e->pack_done[k]) cudaEventDestroy(e->pack_done[k]);
     if (e->copy_done[k]) cudaEventDestroy(e->copy_done[k]);
@@ -557,6 +576,8 @@ VP8R_API void vp8r_engine_destroy(vp8r_engine *e) {
     if (sl.d_status_dev) cudaFree(sl.d_status_dev);
     if (sl.done) cudaEventDestroy(sl.done);
     if (sl.parsed) cudaEventDestroy(sl.parsed);
+    if (sl.modes_done) cudaEventDestroy(sl.modes_done);
+    if (sl.segments_done) cudaEventDestroy(sl.segments_done);
   }
   if (e->h_cjobs) cudaFreeHost(e->h_cjobs);
   if (e->d_cjobs) cudaFree(e->d_cjobs);
@@ -577,7 +598,7 @@ VP8R_API void vp8r_engine_destroy(vp8r_engine *e) {
 
 VP8R_API int vp8r_engine_sync(vp8r_engine *e) {
   if (!e) return VP8R_ERR_INVALID_ARG;
-  CU_TRY(cudaStreamSynchronize(e->st_parse));
+  CU_TRY(SyncParseStreams(e));
   CU_TRY(cudaStreamSynchronize(e->st));
   CU_TRY(cudaStreamSynchronize(e->st_copy));
   for (bool &b : e->copy_busy) b = false;
@@ -606,7 +627,7 @@ VP8R_API int vp8r_stream_open(vp8r_engine *e, vp8r_stream **out) {
 VP8R_API void vp8r_stream_close(vp8r_stream *s) {
   if (!s) return;
   cudaSetDevice(s->eng->device);
-  cudaStreamSynchronize(s->eng->st_parse);  // a parse kernel may still use the stream's segment map
+  SyncParseStreams(s->eng);  // a parse kernel may still use the stream's segment map
   cudaStreamSynchronize(s->eng->st);
   for (auto &sl : s->eng->slots)
     for (auto &p : sl.batch_streams)
@@ -700,6 +721,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
     }
     if (!(f->d_blob && f->d_device == e->device)) arena += FrameDevExtra(f).total;
   }
+  const int slot_index = e->cur_slot;
   Slot &sl = e->slots[e->cur_slot];
   e->cur_slot = (e->cur_slot + 1) % vp8r_engine::kSlots;
   if (sl.pending) {
@@ -733,7 +755,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
   // they overlap the reconstruction kernels of the previous time step on `st`.
   bool deferred = false;
   for (int i = 0; i < n; ++i) deferred |= frames[i]->hdr.tokens_deferred != 0;
-  cudaStream_t front = deferred ? e->st_parse : e->st;
+  cudaStream_t front = deferred ? e->st_parse[slot_index] : e->st;
   {
     ScopedTimer t(e, 3, front);
     for (int i = 0; i < n; ++i) {
@@ -860,7 +882,17 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
   if (any_tokens) {
     CU_TRY(cudaMemsetAsync(sl.d_status_dev, 0, sizeof(int) * n, front));
     ScopedTimer t(e, 5, front);
-    CU_TRY(vp8r::LaunchTokens(sl.d_jobs, n, max_cols, max_mbs, max_parts, any_modes, front));
+    if (any_modes) {
+      // K_modes here, K_segments in batch order on its own stream, then back (see token_kernel.cu)
+      CU_TRY(vp8r::LaunchModes(sl.d_jobs, n, max_cols, max_mbs, front));
+      CU_TRY(cudaEventRecord(sl.modes_done, front));
+      CU_TRY(cudaStreamWaitEvent(e->st_segments, sl.modes_done, 0));
+      CU_TRY(vp8r::LaunchSegments(sl.d_jobs, n, max_mbs, e->st_segments));
+      CU_TRY(cudaEventRecord(sl.segments_done, e->st_segments));
+      CU_TRY(cudaStreamWaitEvent(front, sl.segments_done, 0));
+      e->acc.launches_other += 2;
+    }
+    CU_TRY(vp8r::LaunchTokens(sl.d_jobs, n, max_cols, max_parts, front));
     e->acc.launches_other++;
   }
   if (front != e->st) {
