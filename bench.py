@@ -358,13 +358,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=512, help="independent 1080p streams per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config 3/4/5 block")
-    ap.add_argument("--e2e-parse", default="mix", choices=["host", "tokens", "device", "mix"],
+    ap.add_argument("--e2e-parse", default="device", choices=["host", "tokens", "device", "mix"],
                     help="end-to-end pass: where the bitstream is parsed. host: everything on host threads; tokens: "
                          "first partition on the host, DCT token partitions on the GPU; device: frame headers on the "
-                         "host, all per-macroblock syntax on the GPU; mix (default): tokens on the GPU, macroblock "
+                         "host, all per-macroblock syntax on the GPU (default); mix: tokens on the GPU, macroblock "
                          "headers on the GPU for --device-share of the streams and on host threads for the rest")
     ap.add_argument("--device-share", type=float, default=None,
                     help="mix: share of the streams whose macroblock headers are decoded on the GPU "
@@ -608,7 +608,8 @@ def main():
         elif host_seconds.get("parse", 0) > 0.5 * e2e_s / max(1, args.e2e_steps):
             e["limiter"] = "host threads: frame-header / first-partition parse on the cores this rank gets"
         else:
-            e["limiter"] = "device-side parse kernel (one lane per bool-coded partition) sharing the SMs with the reconstruction kernels"
+            e["limiter"] = ("device-side parse kernels (one single-lane warp per bool-coded partition: latency-bound chains whose registers "
+                            "fill the SMs) sharing the GPU with the reconstruction kernels; read-back at %.0f %% of its ceiling" % (100 * (e["frac_of_d2h_ceiling"] or 0)))
         print(json.dumps(line))
         if parity is not None and not parity["ok"]:
             raise SystemExit("bench: the GPU output differs from the reference decoder on the benched workload")

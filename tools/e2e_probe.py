@@ -15,7 +15,7 @@ with ThreadPoolExecutor(max_workers=os.cpu_count()) as ex:
 payloads = [vp8_b200.read_ivf(p)[1] for p in paths]
 payloads = [payloads[k % DISTINCT] for k in range(S)]
 shutil.rmtree(tmp, ignore_errors=True)
-stream = torch.cuda.Stream()
+stream = torch.cuda.Stream(priority=int(os.environ.get('PROBE_PRIO', '0')))  # -1: high
 eng = vp8_b200.Engine(0, cuda_stream=stream.cuda_stream)
 eng.set_timing(True)
 DEPTH = int(sys.argv[4]) if len(sys.argv) > 4 else 4

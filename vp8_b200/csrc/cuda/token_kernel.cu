@@ -199,6 +199,42 @@ struct BoolDec {
   __device__ __forceinline__ int BytesConsumed() const { return 2 + ((8 * loaded - avail) >> 3); }
 };
 
+// The same reader with the next word fetched ahead of its use (TokenWarpKernel: a load that a lane waits for
+// inside a step stalls all 32 chains of the warp, and some lane refills in every other step).
+struct BoolDecAhead : BoolDec {
+  unsigned ahead;  // Word(next), already loaded
+  __device__ __forceinline__ void RefillAhead() {
+    const unsigned w = __byte_perm(ahead, 0, 0x0123);
+    ++next;
+    ahead = Word(next);
+    win |= (unsigned long long)w << (32 - avail);
+    avail += 32;
+    loaded += 4;
+  }
+  __device__ __forceinline__ void InitAhead(const unsigned char *raw, unsigned off, const unsigned char *lim) {
+    Init(raw, off, lim);
+    ahead = Word(next);
+  }
+  __device__ __forceinline__ int BitAhead(unsigned prob) {
+    const unsigned split = 1u + (((range - 1u) * prob) >> 8);
+    const unsigned big = split << 24;
+    unsigned hi = (unsigned)(win >> 32);
+    const int bit = hi >= big;
+    if (bit) {
+      hi -= big;
+      range -= split;
+    } else {
+      range = split;
+    }
+    const int sh = __clz(range) - 24;
+    range <<= sh;
+    win = (((unsigned long long)hi << 32) | (unsigned)win) << sh;
+    avail -= sh;
+    if (avail <= 32) RefillAhead();
+    return bit;
+  }
+};
+
 struct TokenShared {
   unsigned char probs[4 * 8 * 3 * 11];
   int progress[8];      // progress[w]: macroblocks finished by partition w, counted along its rows
@@ -651,7 +687,9 @@ __global__ void __launch_bounds__(256) SegmentKernel(const DevFrameJob *__restri
 // with the reconstruction kernels of the previous time step.  (A register cap was tried: spills in the serial
 // chain cost more than the occupancy won.)
 // kBlockWarps / kMinBlocks: launch bounds (VP8R_TOKEN_MINBLOCKS, measured in profiles/r2_summary.md).
-template <int kBlockWarps, int kMinBlocks>
+// kLanes: the partitions of a frame are LANES of one warp that diverge for good (independent thread scheduling
+// interleaves them), instead of one warp each: a quarter of the registers per frame for four partitions.
+template <int kBlockWarps, int kMinBlocks, bool kLanes = false>
 __global__ void __launch_bounds__(kBlockWarps * 32, kMinBlocks) TokenKernel(const DevFrameJob *__restrict__ jobs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const DevFrameJob &job = jobs[blockIdx.x];
@@ -668,8 +706,8 @@ __global__ void __launch_bounds__(kBlockWarps * 32, kMinBlocks) TokenKernel(cons
   for (int i = threadIdx.x; i < 8 * 16; i += blockDim.x) (&sh.blk[0][0])[i] = 0;
   __syncthreads();
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane != 0) return;
+  const int warp = kLanes ? (int)threadIdx.x : (int)(threadIdx.x >> 5);  // = the partition of this thread
+  if (!kLanes && (threadIdx.x & 31) != 0) return;
   const int n_parts = (int)__ldg(&th->n_parts);
   if (warp >= n_parts) return;
 
@@ -791,6 +829,271 @@ __global__ void __launch_bounds__(kBlockWarps * 32, kMinBlocks) TokenKernel(cons
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// K_tokens, warp-synchronous form: 32 token partitions (of 32 / kP frames) per warp, one per lane.
+//
+// A partition is a serial chain, and a warp that runs ONE chain (TokenKernel above) spends an issue slot per
+// instruction of that chain: measured 1490 warp instructions per macroblock, 45 % of all instructions of a
+// device-parsed time step (profiles/r2_summary.md).  Here every lane carries its own chain through the same
+// instruction stream: the decoder is written as an automaton whose step is "one boolean", so that the bulk of the
+// work (the boolean itself, the probability fetch, the token tree as a table walk) is executed once per warp for 32
+// chains.  What is specific to a chain's position (start of a macroblock, start / end of a block, the cat-N extra
+// bits, the emission of a coefficient) sits in short predicated sections that the warp runs when at least one
+// lane is there.  A lane whose macroblock waits for the row above (another lane of the same warp: all partitions
+// of a frame are neighbours) simply idles that step; __syncwarp() at the top of the step orders the shared-memory
+// hand-over.  Same bit sequence, same contexts, same outputs as TokenKernel (src/bitstream_parser.cc:466-537,
+// 572-621 of the reference): the parity tests run both.
+template <int kP>
+__global__ void __launch_bounds__(32) TokenWarpKernel(const DevFrameJob *__restrict__ jobs, int n_frames, int max_cols) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int kFrames = 32 / kP;
+  constexpr unsigned kProbBytes = 4 * 8 * 3 * 11;  // 1056
+  const int lane = threadIdx.x;
+  const int fslot = lane / kP, part = lane % kP;
+  const int frame = blockIdx.x * kFrames + fslot;
+  const unsigned above_bytes = ((unsigned)max_cols * 2u + 15u) & ~15u;
+  const unsigned per_frame = kProbBytes + 32u + above_bytes;
+  short *const blk = reinterpret_cast<short *>(smem_raw) + lane * 16;       // staging of this lane's block
+  unsigned char *const cat_tab = smem_raw + 1024;                            // c_cat, 6 x 12
+  unsigned char *const fbase = smem_raw + 1024 + 80 + (unsigned)fslot * per_frame;
+  unsigned char *const probs = fbase;
+  volatile int *const prog = reinterpret_cast<volatile int *>(fbase + kProbBytes);
+  unsigned short *const above = reinterpret_cast<unsigned short *>(fbase + kProbBytes + 32);
+
+  // ---- set-up: the frames' probabilities, zeroed contexts ----
+  for (int i = lane; i < 32 * 16 / 2; i += 32) reinterpret_cast<unsigned *>(smem_raw)[i] = 0;
+  for (int i = lane; i < 72; i += 32) cat_tab[i] = (&c_cat[0][0])[i];
+  for (int f = 0; f < kFrames; ++f) {
+    const int fr = blockIdx.x * kFrames + f;
+    unsigned char *fb = smem_raw + 1024 + 80 + (unsigned)f * per_frame;
+    const bool have = fr < n_frames && jobs[fr].tok_hdr != nullptr;
+    if (have) {
+      const vp8r_token_hdr *th = reinterpret_cast<const vp8r_token_hdr *>(jobs[fr].tok_hdr);
+      for (int i = lane; i < (int)kProbBytes / 4; i += 32)
+        reinterpret_cast<unsigned *>(fb)[i] = __ldg(reinterpret_cast<const unsigned *>(th->coef_probs) + i);
+    }
+    for (int i = lane; i < (int)(32u + above_bytes) / 4; i += 32) reinterpret_cast<unsigned *>(fb + kProbBytes)[i] = 0;
+  }
+  __syncwarp();
+
+  // ---- this lane's chain ----
+  enum { ST_MB = 0, ST_BLOCK = 1, ST_TOK = 2, ST_DONE = 3 };
+  enum { T_EOB = 0, T_ZERO, T_ONE, T_3, T_4, T_5, T_6, T_7, T_8, T_9, T_10, T_EXTRA, T_SIGN, T_END, T_ZADV };
+  // next token state by (state, boolean), 4 bits per state
+  constexpr unsigned long long kNext0 = 0x0ull | ((unsigned long long)T_END << 0) | ((unsigned long long)T_ZADV << 4) |
+                                        ((unsigned long long)T_SIGN << 8) | ((unsigned long long)T_4 << 12) |
+                                        ((unsigned long long)T_SIGN << 16) | ((unsigned long long)T_SIGN << 20) |
+                                        ((unsigned long long)T_7 << 24) | ((unsigned long long)T_EXTRA << 28) |
+                                        ((unsigned long long)T_9 << 32) | ((unsigned long long)T_EXTRA << 36) |
+                                        ((unsigned long long)T_EXTRA << 40) | ((unsigned long long)T_EXTRA << 44) |
+                                        ((unsigned long long)T_EOB << 48);
+  constexpr unsigned long long kNext1 = 0x0ull | ((unsigned long long)T_ZERO << 0) | ((unsigned long long)T_ONE << 4) |
+                                        ((unsigned long long)T_3 << 8) | ((unsigned long long)T_6 << 12) |
+                                        ((unsigned long long)T_5 << 16) | ((unsigned long long)T_SIGN << 20) |
+                                        ((unsigned long long)T_8 << 24) | ((unsigned long long)T_EXTRA << 28) |
+                                        ((unsigned long long)T_10 << 32) | ((unsigned long long)T_EXTRA << 36) |
+                                        ((unsigned long long)T_EXTRA << 40) | ((unsigned long long)T_EXTRA << 44) |
+                                        ((unsigned long long)T_EOB << 48);
+  // c_zigzag as 16 x 4 bits, c_band as 17 x 3 bits (entry i at bit 4 i / 3 i)
+  constexpr unsigned long long zig = 0xfeb7adc963258410ull, band = 0xfb6db6d66688ull;
+
+  const bool have_frame = frame < n_frames && jobs[frame].tok_hdr != nullptr;
+  const DevFrameJob *jobp = jobs + (have_frame ? frame : 0);
+  const vp8r_token_hdr *th = reinterpret_cast<const vp8r_token_hdr *>(jobp->tok_hdr);
+  const int n_parts = have_frame ? (int)__ldg(&th->n_parts) : 0;
+  const bool active = have_frame && part < n_parts;
+  const int cols = jobp->mb_cols, rows = jobp->mb_rows;
+  vp8r_mb_info *const mbs = const_cast<vp8r_mb_info *>(jobp->mbs);
+  int16_t *const coef_area = const_cast<int16_t *>(jobp->payload) + (size_t)jobp->coef_base * 16;
+  const unsigned coef_base = jobp->coef_base;
+  unsigned part_size = 0;
+  BoolDecAhead bd;
+  bd.next = bd.end = nullptr;
+  bd.win = 0;
+  bd.avail = 64;
+  bd.range = 255;
+  bd.loaded = 0;
+  bd.ahead = 0;
+  if (active) {
+    const unsigned char *raw = reinterpret_cast<const unsigned char *>(th) + sizeof(vp8r_token_hdr);
+    part_size = __ldg(&th->part_size[part]);
+    const unsigned off = __ldg(&th->part_off[part]);
+    bd.InitAhead(raw, off, raw + off + part_size);
+  }
+  const int prev_part = active ? (part + n_parts - 1) % n_parts : 0;
+
+  int st = active && part < rows ? ST_MB : ST_DONE;
+  int r = part, c = 0, k = 0;
+  unsigned left = 0, stored_row = 0;
+  bool used = false;
+  // the record of the macroblock to come is fetched one macroblock ahead: a load from L2 inside the step would
+  // stall all 32 chains
+  unsigned flags_next = st == ST_MB ? mbs[(size_t)r * cols].flags : 0u;
+  // macroblock
+  unsigned flags = 0, abv = 0, ca = 0, cl = 0, raw_nz = 0, dq_nz = 0, stored = 0, new_above = 0, new_left = 0;
+  unsigned dq_y1 = 0, dq_y2 = 0, dq_uv = 0;  // dc | ac << 16
+  bool has_y2 = false;
+  // block
+  int b = 0, n = 0, tok = 0, v = 0, extra = 0, cat = 0, remaining = 0;
+  unsigned q = 0, dq_pair = 0;
+  bool any = false, dq_any = false;
+  const unsigned char *p = probs, *bands = probs;
+
+  constexpr unsigned kInnerAboveY = 0x0001ffe0u, kInnerAboveC = (3u << 19) | (3u << 23);
+  constexpr unsigned kInnerLeft = 0x0001dddcu | (1u << 18) | (1u << 20) | (1u << 22) | (1u << 24);
+
+  for (;;) {
+    __syncwarp();
+    if (__all_sync(0xffffffffu, st == ST_DONE)) break;
+    bool finish = false;
+
+    if (st == ST_MB) {
+      bool ready = true;
+      if (r > 0 && n_parts > 1) ready = prog[prev_part] >= (part ? k : k - 1) * cols + c + 1;
+      if (ready) {
+        flags = flags_next;
+        has_y2 = (flags & VP8R_MB_HAS_Y2) != 0;
+        abv = above[c];
+        if (flags & VP8R_MB_SKIP_COEF) {
+          new_above = has_y2 ? 0u : (abv & 0x100u);
+          new_left = has_y2 ? 0u : (left & 0x100u);
+          finish = true;
+        } else {
+          used = true;
+          const short *dq = jobp->dq[(flags >> VP8R_MB_QSEG_SHIFT) & 3];
+          dq_y1 = (unsigned)(unsigned short)dq[VP8R_DQ_Y1_DC] | ((unsigned)(unsigned short)dq[VP8R_DQ_Y1_AC] << 16);
+          dq_y2 = (unsigned)(unsigned short)dq[VP8R_DQ_Y2_DC] | ((unsigned)(unsigned short)dq[VP8R_DQ_Y2_AC] << 16);
+          dq_uv = (unsigned)(unsigned short)dq[VP8R_DQ_UV_DC] | ((unsigned)(unsigned short)dq[VP8R_DQ_UV_AC] << 16);
+          raw_nz = dq_nz = 0;
+          stored = 0;
+          ca = ((abv >> 8) & 1u) | ((abv & 0xfu) << 1) | (((abv >> 4) & 3u) << 17) | (((abv >> 6) & 3u) << 21);
+          cl = ((left >> 8) & 1u) | ((left & 1u) << 1) | (((left >> 1) & 1u) << 5) | (((left >> 2) & 1u) << 9) |
+               (((left >> 3) & 1u) << 13) | (((left >> 4) & 1u) << 17) | (((left >> 5) & 1u) << 19) |
+               (((left >> 6) & 1u) << 21) | (((left >> 7) & 1u) << 23);
+          b = has_y2 ? 0 : 1;
+          st = ST_BLOCK;
+        }
+      }
+    }
+
+    if (st == ST_BLOCK) {
+      const int ctx = (int)(((ca >> b) & 1u) + ((cl >> b) & 1u));
+      int type;
+      if (b == 0) {
+        type = 1; n = 0; dq_pair = dq_y2;
+      } else if (b <= 16) {
+        type = has_y2 ? 0 : 3; n = has_y2 ? 1 : 0; dq_pair = dq_y1;
+      } else {
+        type = 2; n = 0; dq_pair = dq_uv;
+      }
+      bands = probs + type * (8 * 3 * 11);
+      p = bands + (n * 3 + ctx) * 11;  // the band of coefficient 0 / 1 is 0 / 1
+      any = dq_any = false;
+      tok = T_EOB;
+      st = ST_TOK;
+    }
+
+    if (st == ST_TOK) {
+      const unsigned char *pa = tok <= T_10 ? p + tok : cat_tab + q;
+      unsigned prob = *pa;
+      if (tok == T_SIGN) prob = 128;
+      const int bit = bd.BitAhead(prob);
+      int nt = (int)(((bit ? kNext1 : kNext0) >> (4 * tok)) & 15ull);
+      int nctx = 0;
+      bool adv = nt == T_ZADV;
+      if (tok == T_EXTRA) {
+        extra = extra + extra + bit;
+        ++q;
+        if (--remaining == 0) {
+          v = 3 + (2 << cat) + extra;
+          nt = T_SIGN;
+        }
+      } else if (nt == T_EXTRA) {  // from T_7 / T_9 / T_10
+        cat = (tok == T_7 ? 0 : (tok == T_9 ? 2 : 4)) + bit;
+        q = (unsigned)cat * 12u;
+        remaining = (int)((0xb54321u >> (4 * cat)) & 15u);
+        extra = 0;
+      } else if (nt == T_SIGN) {  // from T_ONE / T_4 / T_5
+        v = tok == T_ONE ? 1 : tok - 2 + bit;
+      }
+      if (tok == T_SIGN) {
+        const int val = bit ? -v : v;
+        blk[(int)((zig >> (4 * n)) & 15ull)] = (short)val;
+        any = true;
+        const int f = (int)(short)(n == 0 ? (dq_pair & 0xffffu) : (dq_pair >> 16));
+        if ((short)(val * f) != 0) dq_any = true;
+        nctx = v > 1 ? 2 : 1;
+        adv = true;
+      }
+      if (adv) {
+        ++n;
+        p = bands + ((int)((band >> (3 * n)) & 7ull) * 3 + nctx) * 11;
+        nt = n == 16 ? T_END : (tok == T_SIGN ? T_EOB : T_ZERO);
+      }
+      tok = nt;
+      if (nt == T_END) {
+        if (any) {
+          raw_nz |= 1u << b;
+          ca |= b <= 16 ? (16u << b) & kInnerAboveY : (4u << b) & kInnerAboveC;
+          cl |= (2u << b) & kInnerLeft;
+          int16_t *out = coef_area + ((size_t)r * cols * 25u + stored_row + stored) * 16;
+          const uint4 lo = *reinterpret_cast<const uint4 *>(blk), hi = *reinterpret_cast<const uint4 *>(blk + 8);
+          *reinterpret_cast<uint4 *>(out) = lo;
+          *reinterpret_cast<uint4 *>(out + 8) = hi;
+          *reinterpret_cast<uint4 *>(blk) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4 *>(blk + 8) = make_uint4(0, 0, 0, 0);
+          ++stored;
+        }
+        if (dq_any) dq_nz |= 1u << b;
+        ++b;
+        st = ST_BLOCK;
+        if (b == 25) {
+          new_above = ((dq_nz >> 13) & 0xfu) | (((dq_nz >> 19) & 3u) << 4) | (((dq_nz >> 23) & 3u) << 6);
+          new_left = ((dq_nz >> 4) & 1u) | (((dq_nz >> 8) & 1u) << 1) | (((dq_nz >> 12) & 1u) << 2) | (((dq_nz >> 16) & 1u) << 3) |
+                     (((dq_nz >> 18) & 1u) << 4) | (((dq_nz >> 20) & 1u) << 5) | (((dq_nz >> 22) & 1u) << 6) |
+                     (((dq_nz >> 24) & 1u) << 7);
+          if (has_y2) {
+            new_above |= (dq_nz & 1u) << 8;
+            new_left |= (dq_nz & 1u) << 8;
+          } else {
+            new_above |= abv & 0x100u;
+            new_left |= left & 0x100u;
+          }
+          if (raw_nz) {
+            const size_t idx = (size_t)r * cols + c;
+            mbs[idx].coef_mask = raw_nz;
+            mbs[idx].coef_offset = coef_base + (unsigned)r * (unsigned)cols * 25u + stored_row;
+            mbs[idx].flags = flags | VP8R_MB_LF_INNER;
+          }
+          stored_row += stored;
+          finish = true;
+        }
+      }
+    }
+
+    if (finish) {
+      above[c] = (unsigned short)new_above;
+      left = new_left;
+      prog[part] = k * cols + c + 1;
+      st = ST_MB;
+      if (++c == cols) {
+        c = 0;
+        r += n_parts;
+        ++k;
+        left = 0;
+        stored_row = 0;
+        if (r >= rows) st = ST_DONE;
+      }
+      if (st == ST_MB) flags_next = mbs[(size_t)r * cols + c].flags;
+    }
+  }
+  if (active && used && bd.BytesConsumed() > (int)part_size && jobp->status) {
+    atomicOr(jobp->status, 1);
+    if (jobp->status_host) atomicOr(jobp->status_host, 1);
+  }
+}
+
 cudaError_t InitParseTables() {
   ModeTables t = kModeTablesInit;
   static_assert(sizeof(t.kf_bmode) == sizeof(host_tables::kKfBmode), "kf_bmode size");
@@ -830,8 +1133,30 @@ cudaError_t LaunchSegments(const DevFrameJob *jobs, int n_frames, int max_mbs, c
 }
 
 cudaError_t LaunchTokens(const DevFrameJob *jobs, int n_frames, int max_cols, int max_parts, cudaStream_t st) {
-  const size_t smem = TokenSmem(max_cols);
   max_parts = max_parts < 1 ? 1 : (max_parts > kTokenWarps ? kTokenWarps : max_parts);
+  // VP8R_TOKENS=chain: one warp per partition (TokenKernel); default: 32 partitions per warp (TokenWarpKernel)
+  const char *form = std::getenv("VP8R_TOKENS");
+  if (form && form[0] == 'l') {
+    const size_t smem = TokenSmem(max_cols);
+    static size_t lmarks[64] = {};
+    cudaError_t e = EnsureSmem(TokenKernel<1, 1, true>, smem, lmarks);
+    if (e != cudaSuccess) return e;
+    TokenKernel<1, 1, true><<<n_frames, 32, smem, st>>>(jobs);
+    return cudaGetLastError();
+  }
+  if (form && form[0] == 'w') {
+    const int kp = max_parts <= 1 ? 1 : (max_parts <= 2 ? 2 : (max_parts <= 4 ? 4 : 8));
+    const int frames_per_warp = 32 / kp;
+    const size_t per_frame = 4 * 8 * 3 * 11 + 32 + ((size_t(max_cols) * 2 + 15) & ~size_t(15));
+    const size_t wsmem = 1024 + 80 + frames_per_warp * per_frame;
+    void (*wk)(const DevFrameJob *, int, int) = kp == 1 ? TokenWarpKernel<1> : kp == 2 ? TokenWarpKernel<2> : kp == 4 ? TokenWarpKernel<4> : TokenWarpKernel<8>;
+    static size_t wmarks[4][64] = {};
+    cudaError_t e = EnsureSmem(wk, wsmem, wmarks[kp == 1 ? 0 : kp == 2 ? 1 : kp == 4 ? 2 : 3]);
+    if (e != cudaSuccess) return e;
+    wk<<<(n_frames + frames_per_warp - 1) / frames_per_warp, 32, wsmem, st>>>(jobs, n_frames, max_cols);
+    return cudaGetLastError();
+  }
+  const size_t smem = TokenSmem(max_cols);
   static const int min_blocks = [] { const char *v = std::getenv("VP8R_TOKEN_MINBLOCKS"); return v ? std::atoi(v) : 0; }();
   // (min blocks 0 = "unspecified" makes ptxas settle on 48 registers with spills for this kernel; 1 gives 72, none)
   const int variant = max_parts <= 4 ? (min_blocks >= 8 ? 2 : 1) : 0;
