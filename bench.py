@@ -342,13 +342,12 @@ def secondary_roofline(value_frames_per_s, world, sm_mhz):
         inst = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["warp_instructions_per_frame"]
     except Exception:
         return None
-    per_frame = float(sum(inst[k] for k in ("inter", "intra", "filter") if k in inst))
+    per_frame = float(sum(v for v in inst.values() if isinstance(v, (int, float))))
     clock = (sm_mhz or 1965) * 1e6
     peak = 148 * 4 * clock
     achieved = per_frame * value_frames_per_s / max(1, world)
     return {"bound": "issue", "warp_inst_per_frame": per_frame, "by_kernel": inst, "peak_warp_inst_per_s": peak,
-            "achieved_warp_inst_per_s": achieved, "frac": achieved / peak,
-            "source": inst.get("source", "profiles/ncu_traffic.json")}
+            "achieved_warp_inst_per_s": achieved, "frac": achieved / peak}
 
 
 def main():
