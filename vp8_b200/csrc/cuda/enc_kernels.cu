@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kEncWarps * 32) EncodeIntraKernel(const DevFra
   for (int i = threadIdx.x; i < rows; i += blockDim.x) progress[i] = 0;
   __syncthreads();
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // from lane 0: known to be warp-uniform
   short *const y2_slot = scratch[warp].y2;
   vp8r_mb_info *const mbs = const_cast<vp8r_mb_info *>(job.mbs);
   int16_t *const payload = const_cast<int16_t *>(job.payload);

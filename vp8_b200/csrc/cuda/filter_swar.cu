@@ -163,7 +163,7 @@ __device__ __forceinline__ void FilterBandSwar(const DevFrameJob *__restrict__ j
   constexpr int kN = 4 * NB;            // macroblock size in this plane
   constexpr int kRegion = NB + 1;       // 16-byte chunks between the regions of a slot (one pad chunk)
   constexpr int kSlot = 4 * kRegion;    // chunks per slot; = 4 (mod 8) so that two slots never share a bank group
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // from lane 0: known to be warp-uniform
   const int slot = lane >> 2, u = lane & 3;
   const int pl = NB == 4 ? 0 : (u >> 1);   // chroma: 0 = U, 1 = V
   const int sub = NB == 4 ? u : (u & 1);   // row group (vertical edges) / column group (horizontal edges)

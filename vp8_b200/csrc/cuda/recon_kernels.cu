@@ -357,7 +357,9 @@ __device__ __forceinline__ WholeMbGeometry WholeGeometry(const DevFrameJob &job,
   WholeMbGeometry g;
   const int mvr = mb.mv[0], mvc = mb.mv[1];
   const int sr = s16(4 * mvr), sc = s16(4 * mvc);
-  int cmr = (sr >= 0 ? (sr + 4) : (sr - 4)) / 8, cmc = (sc >= 0 ? (sc + 4) : (sc - 4)) / 8;
+  // (x + sign(x) 4) / 8, truncating: on magnitudes
+  const int ar = (abs(sr) + 4) >> 3, ac = (abs(sc) + 4) >> 3;
+  int cmr = sr < 0 ? -ar : ar, cmc = sc < 0 ? -ac : ac;
   if (job.version == 3) {
     cmr &= ~7;
     cmc &= ~7;
@@ -557,7 +559,8 @@ constexpr int kInterWarps = 4;
 #endif
 // One inter macroblock by one warp.
 template <bool kTma>
-__device__ __forceinline__ void InterOneMacroblock(const DevFrameJob &job, int mb_index, int lane, InterScratch &scratch, InterTile *tile) {
+__device__ __forceinline__ void InterOneMacroblock(const DevFrameJob &job, int mb_r, int mb_c, int lane, InterScratch &scratch, InterTile *tile) {
+  const int mb_index = mb_r * job.mb_cols + mb_c;
   vp8r_mb_info mb;
   {
     const int4 *p = reinterpret_cast<const int4 *>(job.mbs + mb_index);
@@ -568,12 +571,13 @@ __device__ __forceinline__ void InterOneMacroblock(const DevFrameJob &job, int m
   }
   if (!(mb.flags & VP8R_MB_IS_INTER)) return;
 
-  const int mb_r = mb_index / job.mb_cols, mb_c = mb_index - mb_r * job.mb_cols;
   const bool split = ((mb.flags >> VP8R_MB_MODE_SHIFT) & 7) == 4;
   WholeMbGeometry geo{};
   if (!split) {
     geo = WholeGeometry(job, mb, mb_r, mb_c);
     if (kTma && lane == 0) {  // the three windows are on their way while the warp computes the residual
+      // (all operands are warp-uniform and, the warp index being read from lane 0 in the kernel, known to be: they
+      // live in uniform registers and each UTMALDG is issued directly, not through an elect / broadcast loop)
       const DevTensorMap *maps = job.ref_tmap[(mb.flags >> VP8R_MB_REF_SHIFT) & 3];
       MbarExpectTx(&tile->bar, kInterTileTxBytes);
       TmaLoad2D(tile->luma, maps + 0, (geo.wx + kBorder) & ~15, geo.wy + kBorder, &tile->bar);
@@ -730,31 +734,36 @@ __device__ __forceinline__ void InterOneMacroblock(const DevFrameJob &job, int m
 #define VP8R_INTER_MBS_PER_WARP 1
 #endif
 constexpr int kInterMbsPerWarp = VP8R_INTER_MBS_PER_WARP;
+// grid = (macroblock columns / (warps x macroblocks per warp), macroblock rows, frames): a warp's macroblock
+// coordinates come from the block indices (a linear index cost ~24 instructions per macroblock for the division)
 template <bool kTma>
 __global__ void __launch_bounds__(kInterWarps * 32, VP8R_INTER_MINBLOCKS) InterKernel(const DevFrameJob *__restrict__ jobs) {
   __shared__ InterScratch s_scratch[kInterWarps];
   __shared__ InterTile s_tile[kTma ? kInterWarps : 1];
-  const DevFrameJob &job = jobs[blockIdx.y];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const DevFrameJob &job = jobs[blockIdx.z];
+  // (read from lane 0: tells the compiler that the warp index, and every address derived from it, is warp-uniform)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int mb_r = blockIdx.y, cols = job.mb_cols;
+  const int first_c = (blockIdx.x * kInterWarps + warp) * kInterMbsPerWarp;
+  if (mb_r >= job.mb_rows || first_c >= cols) return;
   if (JobFailed(job) || JobInter(job) == 0) return;
   if (kTma) {  // every warp fetches one macroblock: its barrier completes phase 0 exactly once
     if (lane == 0) MbarInit(&s_tile[warp].bar, 1);
     __syncwarp();
   }
-  const int n_mb = job.mb_cols * job.mb_rows;
-  const int first = (blockIdx.x * kInterWarps + warp) * kInterMbsPerWarp;
 #pragma unroll 1
   for (int k = 0; k < kInterMbsPerWarp; ++k) {
-    if (first + k >= n_mb) break;
-    InterOneMacroblock<kTma>(job, first + k, lane, s_scratch[warp], &s_tile[kTma ? warp : 0]);
+    if (first_c + k >= cols) break;
+    InterOneMacroblock<kTma>(job, mb_r, first_c + k, lane, s_scratch[warp], &s_tile[kTma ? warp : 0]);
     __syncwarp();  // the scratch is rewritten by the next macroblock
   }
 }
 
-cudaError_t LaunchInter(const DevFrameJob *jobs, int n_frames, int max_mbs, cudaStream_t st, bool tma) {
+cudaError_t LaunchInter(const DevFrameJob *jobs, int n_frames, int max_cols, int max_rows, cudaStream_t st, bool tma) {
   static_assert(kInterMbsPerWarp == 1, "the TMA path arms each warp's barrier once");
   const int per_cta = kInterWarps * kInterMbsPerWarp;
-  dim3 grid((max_mbs + per_cta - 1) / per_cta, n_frames);
+  if (max_rows > 65535 || n_frames > 65535) return cudaErrorInvalidValue;
+  dim3 grid((max_cols + per_cta - 1) / per_cta, max_rows, n_frames);
   if (tma) InterKernel<true><<<grid, kInterWarps * 32, 0, st>>>(jobs);
   else InterKernel<false><<<grid, kInterWarps * 32, 0, st>>>(jobs);
   return cudaGetLastError();
@@ -935,6 +944,13 @@ __device__ __forceinline__ void IntraMacroblock(const DevFrameJob &job, int r, i
   {
     const int4 *p = reinterpret_cast<const int4 *>(job.mbs + r * job.mb_cols + c);
     int4 a = __ldg(p), b = __ldg(p + 1);
+#ifndef VP8R_INTER_NO_UNIFORM_RECORD
+    // every lane holds the same record; reading it from lane 0 makes that known to the compiler (uniform branches,
+    // uniform-datapath address arithmetic)
+    a.x = __shfl_sync(0xffffffffu, a.x, 0); a.y = __shfl_sync(0xffffffffu, a.y, 0);
+    a.z = __shfl_sync(0xffffffffu, a.z, 0); a.w = __shfl_sync(0xffffffffu, a.w, 0);
+    b.x = __shfl_sync(0xffffffffu, b.x, 0); b.y = __shfl_sync(0xffffffffu, b.y, 0);
+#endif
     mb.flags = a.x; mb.coef_mask = a.y; mb.coef_offset = a.z;
     mb.aux[0] = b.x; mb.aux[1] = b.y;
   }
@@ -966,7 +982,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32) IntraKernel(const DevFrameJob
   for (int i = threadIdx.x; i < 160; i += blockDim.x) lut[i] = c_bpred_lut[i];
   __syncthreads();
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // from lane 0: known to be warp-uniform
   IntraScratch &s = scratch[warp];
   for (int r = warp; r < rows; r += kWaveWarps) {
     for (int c0 = 0; c0 < cols; c0 += 32) {
@@ -997,7 +1013,7 @@ __global__ void __launch_bounds__(kFlatWarps * 32) IntraFlatKernel(const DevFram
   const unsigned first = __ldg(job.intra_levels + level), end = __ldg(job.intra_levels + level + 1);
   for (int i = threadIdx.x; i < 160; i += blockDim.x) lut[i] = c_bpred_lut[i];
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // from lane 0: known to be warp-uniform
   const unsigned slot = first + blockIdx.x * kFlatWarps + warp;
   if (slot >= end) return;
   const unsigned mb_index = __ldg(job.intra_levels + job.n_intra_levels + 1 + slot);
@@ -1018,7 +1034,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32) IntraLevelsKernel(const DevF
   if (n_levels == 0) return;
   for (int i = threadIdx.x; i < 160; i += blockDim.x) lut[i] = c_bpred_lut[i];
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // from lane 0: known to be warp-uniform
   const uint32_t *tab = JobLevelTable(job);
   const uint32_t *order = tab + n_levels + 1;
   for (int level = 0; level < n_levels; ++level) {
@@ -1237,7 +1253,7 @@ __global__ void __launch_bounds__(kFiltWarps * 32, kFiltCtasPerSm) FilterKernel(
   for (int i = threadIdx.x; i < rpb; i += blockDim.x) lprog[i] = 0;
   __syncthreads();
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // from lane 0: known to be warp-uniform
   // Everything read from the job is copied to registers here: the pixel stores below are char-typed
   // and would otherwise force the compiler to reload job fields from global memory after each one.
   const bool simple = job.filter_type != 0;

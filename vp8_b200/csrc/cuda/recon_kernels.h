@@ -113,7 +113,7 @@ inline size_t TokenCoefBlocks(int mb_cols, int mb_rows) { return size_t(mb_cols)
 // K_inter: dequant + IWHT/IDCT + motion compensation + residual add for every inter MB.
 // `tma`: reference windows of macroblocks with one motion vector are staged in shared memory by bulk tensor
 // loads (every job must carry ref_tmap); otherwise by 32-bit loads of the lanes.
-cudaError_t LaunchInter(const DevFrameJob *jobs, int n_frames, int max_mbs, cudaStream_t st, bool tma = false);
+cudaError_t LaunchInter(const DevFrameJob *jobs, int n_frames, int max_cols, int max_rows, cudaStream_t st, bool tma = false);
 // K_intra: dequant + IWHT/IDCT + intra prediction as a per-frame macroblock wavefront.
 cudaError_t LaunchIntra(const DevFrameJob *jobs, int n_frames, int max_rows, cudaStream_t st);
 // Flat intra: every intra MB of dependency level `level` (frames with n_intra_levels > 0).

@@ -747,7 +747,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
   sl.any_status = false;
 
   // Pass 2: jobs + host->device staging.
-  int max_mbs = 0, max_rows = 0, max_cols = 0, max_parts = 1;
+  int max_mbs = 0, max_rows = 0, max_cols = 0, max_cols_all = 0, max_parts = 1;
   bool any_inter = false, any_intra = false, any_wave = false, any_tokens = false, any_modes = false, any_level_walk = false;
   std::vector<int> level_max;  // per dependency level: most intra MBs of that level in any frame
   size_t at = 0, gather_max = 0;
@@ -846,6 +846,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
       j.sharpness = h.sharpness_level;
       max_mbs = std::max(max_mbs, n_mb);
       max_rows = std::max(max_rows, int(h.mb_rows));
+      max_cols_all = std::max(max_cols_all, int(h.mb_cols));
       any_inter |= j.n_inter > 0;
       any_intra |= j.n_intra > 0;
       e->acc.frames++;
@@ -905,7 +906,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
     ScopedTimer t(e, 0);
     bool tma = e->inter_tma;
     for (int i = 0; i < n && tma; ++i) tma = streams[i]->d_tmaps != nullptr;
-    CU_TRY(vp8r::LaunchInter(sl.d_jobs, n, max_mbs, e->st, tma));
+    CU_TRY(vp8r::LaunchInter(sl.d_jobs, n, max_cols_all, max_rows, e->st, tma));
     e->acc.launches_inter++;
   }
   if (any_intra) {
