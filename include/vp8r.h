@@ -286,9 +286,14 @@ VP8R_API int vp8r_read_batch_packed_as(vp8r_engine *e, int n, vp8r_stream *const
  * stream k afterwards holds exactly the frame a decoder makes of the result (vp8r_stream_read_frame returns it, and
  * inter frames decoded next predict from it).  out[k] receives the macroblock records and coefficient blocks (the
  * same structure the parser produces); vp8r_frame_write_bitstream turns it into a VP8 frame.  Synchronous. */
+#define VP8R_ENC_BPRED 1u /* flags: B_PRED is a candidate for every macroblock: its sixteen sub-block modes are picked
+                            one after the other on the reconstructed neighbours (ten predictors by squared error, in
+                            enum order, a later one only when strictly better: PickIntraSubBlockModeSB), and the
+                            macroblock is coded B_PRED when the sum of their errors is strictly below the best 16x16
+                            mode's (PickIntraModeLuma, src/encode_frame.cc:204-238) */
 VP8R_API int vp8r_encode_key_frames(vp8r_engine *e, int n, vp8r_stream *const *streams, const uint8_t *const *i420,
                                     int width, int height, int q_index, int loop_filter_level, int sharpness,
-                                    vp8r_frame *const *out);
+                                    unsigned flags, vp8r_frame *const *out);
 /* The inverse of vp8r_parser_parse for key frames: serialises f (key frame, intra macroblocks, one quantiser) into a
  * VP8 frame with one DCT partition and the default token probabilities.  *size receives the number of bytes needed;
  * VP8R_ERR_INVALID_ARG when cap is too small (call again) or the frame cannot be written. */

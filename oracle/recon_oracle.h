@@ -48,6 +48,8 @@ int oracle_pick_chroma_mode(const uint8_t *tu, const uint8_t *tv, int ts, uint8_
 int oracle_pick_sub_mode(const int above[8], const int left[4], int p, const uint8_t target[16], uint32_t err[10]);
 int oracle_encode_key_frame(const uint8_t *sy, const uint8_t *su, const uint8_t *sv, int cols, int rows, const int16_t dq[6],
                             int lf_level, vp8r_mb_info *mbs, int16_t *payload, uint8_t *ry, uint8_t *ru, uint8_t *rv);
+int oracle_encode_key_frame2(const uint8_t *sy, const uint8_t *su, const uint8_t *sv, int cols, int rows, const int16_t dq[6],
+                            int lf_level, vp8r_mb_info *mbs, int16_t *payload, uint8_t *ry, uint8_t *ru, uint8_t *rv, int bpred_search);
 
 #ifdef __cplusplus
 }

@@ -56,8 +56,9 @@ def test_writer_is_the_inverse_of_the_parser(built):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("bpred", [False, True], ids=["16x16", "bpred"])
 @pytest.mark.parametrize("size", [(176, 144), (65, 33), (320, 240), (1280, 720)], ids=lambda s: f"{s[0]}x{s[1]}")
-def test_encoder_matches_oracle_and_reference_decoder(built, size):
+def test_encoder_matches_oracle_and_reference_decoder(built, size, bpred):
     import vp8_b200
     from vp8_b200 import _capi
     w, h = size
@@ -68,7 +69,7 @@ def test_encoder_matches_oracle_and_reference_decoder(built, size):
         for q, lf in ((100, 20), (40, 12), (8, 0)):
             img = _image(w, h, 7 + q)
             st = eng.open_stream()
-            (fr,) = eng.encode_key_frames([st], [img], w, h, q, loop_filter_level=lf)
+            (fr,) = eng.encode_key_frames([st], [img], w, h, q, loop_filter_level=lf, bpred=bpred)
             recon = st.read_frame()
             d = fr.desc()
             cols, rows = d.hdr.mb_cols, d.hdr.mb_rows
@@ -83,12 +84,12 @@ def test_encoder_matches_oracle_and_reference_decoder(built, size):
             mbs = (_capi.MbInfo * (cols * rows))()
             payload = (C.c_int16 * (cols * rows * 25 * 16))()
             ry, ru, rv = np.zeros_like(sy), np.zeros_like(su), np.zeros_like(sv)
-            assert orc.oracle_encode_key_frame(C.c_void_p(sy.ctypes.data), C.c_void_p(su.ctypes.data), C.c_void_p(sv.ctypes.data), cols, rows, dq,
-                                               lf, mbs, payload, C.c_void_p(ry.ctypes.data), C.c_void_p(ru.ctypes.data),
-                                               C.c_void_p(rv.ctypes.data)) == 0
+            assert orc.oracle_encode_key_frame2(C.c_void_p(sy.ctypes.data), C.c_void_p(su.ctypes.data), C.c_void_p(sv.ctypes.data), cols, rows, dq,
+                                                lf, mbs, payload, C.c_void_p(ry.ctypes.data), C.c_void_p(ru.ctypes.data),
+                                                C.c_void_p(rv.ctypes.data), int(bpred)) == 0
             for m in range(cols * rows):
                 a, b = d.mbs[m], mbs[m]
-                assert (a.flags, a.coef_mask, a.coef_offset) == (b.flags, b.coef_mask, b.coef_offset), (q, m)
+                assert (a.flags, a.coef_mask, a.coef_offset, a.aux[0], a.aux[1]) == (b.flags, b.coef_mask, b.coef_offset, b.aux[0], b.aux[1]), (q, m)
                 nb = bin(a.coef_mask).count("1")
                 assert d.payload[a.coef_offset * 16:(a.coef_offset + nb) * 16] == payload[b.coef_offset * 16:(b.coef_offset + nb) * 16], (q, m)
             # (2) the bitstream, decoded by the UNMODIFIED reference decoder, is the frame the encoder holds
@@ -102,7 +103,8 @@ def test_encoder_matches_oracle_and_reference_decoder(built, size):
             back = vp8_b200.Parser().parse(data)
             db = back.desc()
             for m in range(cols * rows):
-                assert (db.mbs[m].flags, db.mbs[m].coef_mask) == (d.mbs[m].flags, d.mbs[m].coef_mask), (q, m)
+                assert (db.mbs[m].flags, db.mbs[m].coef_mask, db.mbs[m].aux[0], db.mbs[m].aux[1]) == \
+                       (d.mbs[m].flags, d.mbs[m].coef_mask, d.mbs[m].aux[0], d.mbs[m].aux[1]), (q, m)
             back.close()
             # (4) finer quantisers are closer to the source
             p = _psnr(recon, img, w * h)

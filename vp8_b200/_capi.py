@@ -72,7 +72,7 @@ SIGNATURES = {
                                   C.POINTER(C.c_size_t), C.c_int]),
     "vp8r_read_batch_packed": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_int]),
     "vp8r_encode_key_frames": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int,
-                                         C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+                                         C.c_int, C.c_int, C.c_uint, C.POINTER(C.c_void_p)]),
     "vp8r_frame_write_bitstream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "vp8r_read_batch_packed_as": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
     "vp8r_stream_read_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

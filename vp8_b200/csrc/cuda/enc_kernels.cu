@@ -2,7 +2,7 @@
 // forward DCT / WHT, quantisation, and the decoder's own reconstruction, one warp per macroblock.
 //
 // Replaces (the reference only sketches its encoder; these are the functions it has):
-//   PickIntraModeLuma (16x16 candidates) / PickIntraModeChroma   src/encode_frame.cc:30-76,204-238
+//   PickIntraModeLuma / PickIntraModeChroma, PickIntraSubBlockModeSB/MB (B_PRED)   src/encode_frame.cc:30-76,109-238
 //   TransformResidual, QuantizeResidualValue                      src/residual.cc:5-40,96-108
 //   DCT, WHT, Quantize                                            src/dct.cc:5-65, src/quantizer.cc:5-8
 // and produces the SAME per-macroblock arrays the decode path consumes (vp8r_mb_info + coefficient blocks), so that
@@ -124,11 +124,21 @@ __device__ __forceinline__ void IwhtE(int *m) {
   }
 }
 
-constexpr int kEncWarps = 32;
+constexpr int kEncWarps = 16;
 
+// Per-warp scratch.  tile: the B_PRED trial's view of the macroblock, as the decoder's PredictBpred lays it out: row 0 =
+// the pixel row above (columns -1..19 at bytes 3..23), byte 3 of rows 1..16 = the column to the left, the macroblock
+// itself at rows 1..16, bytes 4..19.
 struct __align__(16) EncScratch {
   short y2[16];
+  short xfer[16];            // one 4x4 block on its way between the pixel lanes and the transform lane
+  short cand[16][16];        // quantised blocks of the B_PRED trial
+  unsigned char tile[17][32];
 };
+
+// B_PRED gather table, as recon_kernels.cu's c_bpred_lut: [mode][pixel] -> i0 | i1<<4 | i2<<8 | kind<<12 over the edge
+// array E = {L3,L2,L1,L0,P,A0..A7}; kind 0: (E[i0]+2E[i1]+E[i2]+2)>>2, 1: (E[i0]+E[i2]+1)>>1, 2: DC, 3: TM.
+__constant__ unsigned short c_enc_bpred_lut[10 * 16];
 
 // Prediction of this lane's 4x4 block for one 16x16 / 8x8 mode (src/intra_predict.cc:6-98): aw = the four pixels
 // above the block's columns in the macroblock's top edge, l[k] = the pixel left of row k in its left edge.
@@ -161,6 +171,107 @@ __device__ __forceinline__ unsigned Sse4(const unsigned *rows, const unsigned *s
   return e;
 }
 
+
+// B_PRED trial of one macroblock by one warp (src/encode_frame.cc:109-202 for the decision, the decoder's PredictBpred
+// for the edges): sub-block by sub-block in raster order, closed loop inside the macroblock.  Lanes 0..15 are the
+// pixels of the sub-block and try modes 0..4, lanes 16..31 the same pixels for modes 5..9; lane 0 transforms.
+// Returns the sum of the sixteen best prediction errors; s.cand holds the quantised blocks (DC in place), s.tile the
+// reconstruction, aux[2] the sixteen sub-block modes.
+__device__ __forceinline__ unsigned BpredTrial(const DevFrameJob &job, int r, int c, int lane, const unsigned (&src)[4],
+                                               int f_dc, int f_ac, EncScratch &s, const unsigned short *lut, unsigned (&aux)[2]) {
+  const int pitch = job.pitch_y;
+  const uint8_t *mbp = job.cur.y + (ptrdiff_t)(r * 16) * pitch + c * 16;
+  if (lane < 21) {
+    const int col = lane - 1;
+    int v;
+    if (r == 0) v = 127;
+    else if (col < 0) v = c == 0 ? 129 : *reinterpret_cast<const volatile uint8_t *>(mbp - pitch - 1);
+    else if (col >= 16 && c + 1 == job.mb_cols) v = *reinterpret_cast<const volatile uint8_t *>(mbp - pitch + 15);
+    else v = *reinterpret_cast<const volatile uint8_t *>(mbp - pitch + col);
+    s.tile[0][4 + col] = (unsigned char)v;
+  }
+  if (lane < 16) s.tile[1 + lane][3] = (unsigned char)(c == 0 ? 129 : *reinterpret_cast<const volatile uint8_t *>(mbp + (ptrdiff_t)lane * pitch - 1));
+  __syncwarp();
+
+  const int px = lane & 3, py = (lane >> 2) & 3, half = lane >> 4;
+  unsigned total = 0;
+  aux[0] = aux[1] = 0;
+  for (int b = 0; b < 16; ++b) {
+    const int i = b >> 2, j = b & 3;
+    int E = 0;  // edge array, one entry per lane 0..12
+    if (lane < 4) E = s.tile[1 + 4 * i + (3 - lane)][3 + 4 * j];
+    else if (lane < 9) E = s.tile[4 * i][3 + 4 * j + (lane - 4)];
+    else if (lane < 13) E = s.tile[(j == 3) ? 0 : 4 * i][3 + 4 * j + (lane - 4)];
+    const int dc_in = (lane < 4 || (lane >= 5 && lane < 9)) ? E : 0;
+    const int dc = (int)(__reduce_add_sync(0xffffffffu, (unsigned)dc_in) + 4u) >> 3;
+    // this lane's source pixel: block b's rows live in lane b
+    const unsigned w0 = __shfl_sync(0xffffffffu, src[0], b), w1 = __shfl_sync(0xffffffffu, src[1], b);
+    const unsigned w2 = __shfl_sync(0xffffffffu, src[2], b), w3 = __shfl_sync(0xffffffffu, src[3], b);
+    const unsigned wsel = py == 0 ? w0 : (py == 1 ? w1 : (py == 2 ? w2 : w3));
+    const int pix = (int)((wsel >> (8 * px)) & 0xffu);
+    unsigned best_lo = 0xffffffffu, best_hi = 0xffffffffu;
+    int mode_lo = 0, mode_hi = 5, v_best = 0;
+#pragma unroll 1
+    for (int t = 0; t < 5; ++t) {
+      const unsigned e = lut[(t + 5 * half) * 16 + (lane & 15)];
+      const int x0 = __shfl_sync(0xffffffffu, E, e & 15), x1 = __shfl_sync(0xffffffffu, E, (e >> 4) & 15);
+      const int x2 = __shfl_sync(0xffffffffu, E, (e >> 8) & 15);
+      const int kind = e >> 12;
+      int v;
+      if (kind == 0) v = (x0 + 2 * x1 + x2 + 2) >> 2;
+      else if (kind == 1) v = (x0 + x2 + 1) >> 1;
+      else if (kind == 2) v = dc;
+      else v = clamp255e(x0 + x1 - x2);
+      const int d = v - pix;
+      const unsigned se = (unsigned)(d * d);
+      const unsigned e_lo = __reduce_add_sync(0xffffffffu, half ? 0u : se), e_hi = __reduce_add_sync(0xffffffffu, half ? se : 0u);
+      if (e_lo < best_lo) {
+        best_lo = e_lo;
+        mode_lo = t;
+        if (!half) v_best = v;
+      }
+      if (e_hi < best_hi) {
+        best_hi = e_hi;
+        mode_hi = t + 5;
+        if (half) v_best = v;
+      }
+    }
+    const bool hi_wins = best_hi < best_lo;  // the ten modes in order, a later one only when strictly better
+    const int mode = hi_wins ? mode_hi : mode_lo;
+    total += hi_wins ? best_hi : best_lo;
+    const int pred = __shfl_sync(0xffffffffu, v_best, (lane & 15) + (hi_wins ? 16 : 0));
+    if (b < 8) aux[0] |= (unsigned)mode << (4 * b);
+    else aux[1] |= (unsigned)mode << (4 * (b - 8));
+    if (lane < 16) s.xfer[lane] = (short)(pix - pred);
+    __syncwarp();
+    if (lane == 0) {  // forward transform, quantisation, and the decoder's way back
+      int m[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) m[k] = s.xfer[k];
+      Fdct4x4(m);
+      m[0] = s16e(m[0] / f_dc);
+#pragma unroll
+      for (int k = 1; k < 16; ++k) m[k] = s16e(m[k] / f_ac);
+      uint4 *cand = reinterpret_cast<uint4 *>(s.cand[b]);
+      unsigned w[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) w[k] = ((unsigned)m[2 * k] & 0xffffu) | ((unsigned)m[2 * k + 1] << 16);
+      cand[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      cand[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      m[0] = s16e(m[0] * f_dc);
+#pragma unroll
+      for (int k = 1; k < 16; ++k) m[k] = s16e(m[k] * f_ac);
+      IdctE(m);  // (a block with only its DC comes out as (dc + 4) >> 3 everywhere, the decoder's short cut)
+#pragma unroll
+      for (int k = 0; k < 16; ++k) s.xfer[k] = (short)m[k];
+    }
+    __syncwarp();
+    if (lane < 16) s.tile[1 + 4 * i + py][4 + 4 * j + px] = (unsigned char)clamp255e(s16e(pred + s.xfer[lane]));
+    __syncwarp();
+  }
+  return total;
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(kEncWarps * 32) EncodeIntraKernel(const DevFrameJob *__restrict__ jobs) {
@@ -169,9 +280,12 @@ __global__ void __launch_bounds__(kEncWarps * 32) EncodeIntraKernel(const DevFra
   if (!job.enc_src[0]) return;
   const int rows = job.mb_rows, cols = job.mb_cols;
   volatile int *progress = reinterpret_cast<volatile int *>(smem_raw);
-  EncScratch *scratch = reinterpret_cast<EncScratch *>(smem_raw + ((rows * 4 + 15) & ~15));
+  unsigned short *lut = reinterpret_cast<unsigned short *>(smem_raw + ((rows * 4 + 15) & ~15));
+  EncScratch *scratch = reinterpret_cast<EncScratch *>(reinterpret_cast<unsigned char *>(lut) + 320);
   for (int i = threadIdx.x; i < rows; i += blockDim.x) progress[i] = 0;
+  for (int i = threadIdx.x; i < 160; i += blockDim.x) lut[i] = c_enc_bpred_lut[i];
   __syncthreads();
+  const bool try_bpred = (job.enc_flags & VP8R_ENC_BPRED) != 0;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // from lane 0: known to be warp-uniform
   short *const y2_slot = scratch[warp].y2;
@@ -238,8 +352,9 @@ __global__ void __launch_bounds__(kEncWarps * 32) EncodeIntraKernel(const DevFra
       }
       // ---- mode decision: V, H, DC, TM in the reference's order, a later one only when strictly better ----
       int ymode = 0, uvmode = 0;
+      unsigned best_y = 0xffffffffu;
       {
-        unsigned best_y = 0xffffffffu, best_c = 0xffffffffu;
+        unsigned best_c = 0xffffffffu;
         const int order[4] = {1, 2, 0, 3};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -252,28 +367,46 @@ __global__ void __launch_bounds__(kEncWarps * 32) EncodeIntraKernel(const DevFra
           if (ec < best_c) best_c = ec, uvmode = order[k];
         }
       }
+      // ---- B_PRED last, only when strictly better than the best 16x16 mode (src/encode_frame.cc:233-237) ----
+      bool bpred = false;
+      unsigned aux[2] = {0, 0};
+      if (try_bpred) {
+        const int y1_dc = dq[VP8R_DQ_Y1_DC], y1_ac = dq[VP8R_DQ_Y1_AC];
+        bpred = BpredTrial(job, r, c, lane, src, y1_dc, y1_ac, scratch[warp], lut, aux) < best_y;
+        if (bpred) ymode = 4;
+      }
       // ---- residual, forward transform, quantisation ----
       unsigned pred[4];
       PredictRows(luma ? ymode : uvmode, aw, l, P, dc, pred);
       int m[16];
+      if (bpred && lane <= 24) {  // luma blocks were quantised in the trial (DC in place); there is no Y2 block
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int x = 0; x < 4; ++x) m[4 * k + x] = (int)((src[k] >> (8 * x)) & 0xff) - (int)((pred[k] >> (8 * x)) & 0xff);
-      if (is_block) Fdct4x4(m);
-      if (luma) y2_slot[lane] = (short)m[0];
-      __syncwarp();
-      if (lane == 24) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) m[i] = y2_slot[i];
-        Fwht4x4(m);
+        for (int i = 0; i < 16; ++i) m[i] = (luma) ? scratch[warp].cand[lane][i] : 0;
       }
-      __syncwarp();
+      if (!(bpred && (luma || lane == 24))) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int x = 0; x < 4; ++x) m[4 * k + x] = (int)((src[k] >> (8 * x)) & 0xff) - (int)((pred[k] >> (8 * x)) & 0xff);
+        if (is_block) Fdct4x4(m);
+      }
+      if (!bpred) {
+        if (luma) y2_slot[lane] = (short)m[0];
+        __syncwarp();
+        if (lane == 24) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) m[i] = y2_slot[i];
+          Fwht4x4(m);
+        }
+        __syncwarp();
+      }
       bool nz = false;
       if (lane <= 24) {
-        m[0] = luma ? 0 : s16e(m[0] / f_dc);  // a luma block's DC travels in the Y2 block
+        if (!(bpred && (luma || lane == 24))) {
+          m[0] = luma ? 0 : s16e(m[0] / f_dc);  // a luma block's DC travels in the Y2 block
 #pragma unroll
-        for (int i = 1; i < 16; ++i) m[i] = s16e(m[i] / f_ac);
+          for (int i = 1; i < 16; ++i) m[i] = s16e(m[i] / f_ac);
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) nz |= m[i] != 0;
       }
@@ -292,11 +425,11 @@ __global__ void __launch_bounds__(kEncWarps * 32) EncodeIntraKernel(const DevFra
         dst[1] = make_int4((int)w[4], (int)w[5], (int)w[6], (int)w[7]);
       }
       if (lane == 0) {
-        const unsigned flags = ((unsigned)ymode << VP8R_MB_MODE_SHIFT) | ((unsigned)uvmode << VP8R_MB_UVMODE_SHIFT) | VP8R_MB_HAS_Y2 |
-                               lf_bits | (coef_mask ? VP8R_MB_LF_INNER : 0u);
+        const unsigned flags = ((unsigned)ymode << VP8R_MB_MODE_SHIFT) | ((unsigned)uvmode << VP8R_MB_UVMODE_SHIFT) |
+                               (bpred ? 0u : VP8R_MB_HAS_Y2) | lf_bits | ((coef_mask || bpred) ? VP8R_MB_LF_INNER : 0u);
         int4 *rec = reinterpret_cast<int4 *>(mbs + mb_index);
         rec[0] = make_int4((int)flags, (int)coef_mask, (int)coef_offset, 0);
-        rec[1] = make_int4(0, 0, 0, 0);
+        rec[1] = make_int4(bpred ? (int)aux[0] : 0, bpred ? (int)aux[1] : 0, 0, 0);
       }
       // ---- reconstruction, exactly as the decoder does it from the stored blocks (WarpResidual) ----
       if (lane <= 24) {
@@ -305,6 +438,12 @@ __global__ void __launch_bounds__(kEncWarps * 32) EncodeIntraKernel(const DevFra
         for (int i = 1; i < 16; ++i) m[i] = s16e(m[i] * f_ac);
       }
       bool any = nz && is_block;
+      if (bpred) {  // the luma reconstruction stands in the trial's tile
+        if (lane < 16) {
+          const unsigned *t = reinterpret_cast<const unsigned *>(&scratch[warp].tile[1 + lane][4]);
+          *reinterpret_cast<uint4 *>(mbp + (ptrdiff_t)lane * pitch) = make_uint4(t[0], t[1], t[2], t[3]);
+        }
+      }
       if (coef_mask & 1u) {
         if (lane == 24) {
           IwhtE(m);
@@ -318,7 +457,7 @@ __global__ void __launch_bounds__(kEncWarps * 32) EncodeIntraKernel(const DevFra
         }
         __syncwarp();
       }
-      if (is_block) {
+      if (is_block && !(bpred && luma)) {
         if (any) IdctE(m);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -340,8 +479,12 @@ __global__ void __launch_bounds__(kEncWarps * 32) EncodeIntraKernel(const DevFra
   }
 }
 
+cudaError_t InitEncodeTables(const unsigned short *bpred_lut) {
+  return cudaMemcpyToSymbol(c_enc_bpred_lut, bpred_lut, sizeof(unsigned short) * 160);
+}
+
 cudaError_t LaunchEncodeIntra(const DevFrameJob *jobs, int n_frames, int max_rows, cudaStream_t st) {
-  const size_t smem = ((size_t(max_rows) * 4 + 15) & ~size_t(15)) + sizeof(EncScratch) * kEncWarps;
+  const size_t smem = ((size_t(max_rows) * 4 + 15) & ~size_t(15)) + 320 + sizeof(EncScratch) * kEncWarps;
   EncodeIntraKernel<<<n_frames, kEncWarps * 32, smem, st>>>(jobs);
   return cudaGetLastError();
 }

@@ -111,6 +111,8 @@ cudaError_t InitKernelTables() {
   unsigned short lut[160];
   std::memset(lut, 0, sizeof(lut));
   BuildBpredLut(lut);
+  err = InitEncodeTables(lut);
+  if (err != cudaSuccess) return err;
   return cudaMemcpyToSymbol(c_bpred_lut, lut, sizeof(lut));
 }
 
@@ -944,13 +946,11 @@ __device__ __forceinline__ void IntraMacroblock(const DevFrameJob &job, int r, i
   {
     const int4 *p = reinterpret_cast<const int4 *>(job.mbs + r * job.mb_cols + c);
     int4 a = __ldg(p), b = __ldg(p + 1);
-#ifndef VP8R_INTER_NO_UNIFORM_RECORD
-    // every lane holds the same record; reading it from lane 0 makes that known to the compiler (uniform branches,
-    // uniform-datapath address arithmetic)
+    // every lane holds the same record; reading it from lane 0 makes that known to the compiler where the index came
+    // out of a table (uniform branches, uniform-datapath address arithmetic: IntraLevelsKernel 2800 -> 2168 instructions)
     a.x = __shfl_sync(0xffffffffu, a.x, 0); a.y = __shfl_sync(0xffffffffu, a.y, 0);
     a.z = __shfl_sync(0xffffffffu, a.z, 0); a.w = __shfl_sync(0xffffffffu, a.w, 0);
     b.x = __shfl_sync(0xffffffffu, b.x, 0); b.y = __shfl_sync(0xffffffffu, b.y, 0);
-#endif
     mb.flags = a.x; mb.coef_mask = a.y; mb.coef_offset = a.z;
     mb.aux[0] = b.x; mb.aux[1] = b.y;
   }

@@ -53,7 +53,7 @@ struct DevFrameJob {
   uint8_t key_frame, version, filter_type, lf_level, sharpness;
   uint8_t levels_in_one_launch;  // host-built level table walked by IntraLevelsKernel instead of one launch per level
   uint8_t pack_layout;           // PackKernel: VP8R_LAYOUT_I420 / VP8R_LAYOUT_NV12
-  uint8_t pad[1];
+  uint8_t enc_flags;             // K_encode: VP8R_ENC_*
   // output side (crop / checksum)
   int width, height;
   unsigned long long *checksum;  // optional: receives the I420 checksum
@@ -105,6 +105,7 @@ cudaError_t LaunchModes(const DevFrameJob *jobs, int n_frames, int max_cols, int
 cudaError_t LaunchSegments(const DevFrameJob *jobs, int n_frames, int max_mbs, cudaStream_t st);
 cudaError_t LaunchTokens(const DevFrameJob *jobs, int n_frames, int max_cols, int max_parts, cudaStream_t st);
 cudaError_t InitParseTables();
+cudaError_t InitEncodeTables(const unsigned short *bpred_lut);  // enc_kernels.cu: its copy of the B_PRED gather table
 // Level-scheduled intra prediction of frames whose level table was built on the device: one CTA per
 // frame walks the dependency levels with a block barrier in between.
 cudaError_t LaunchIntraLevels(const DevFrameJob *jobs, int n_frames, cudaStream_t st);

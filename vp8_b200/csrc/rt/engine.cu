@@ -965,7 +965,7 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
 // Row f4: closed-loop key-frame encoder.  Source images are padded to whole macroblocks by replicating the last row /
 // column (what an encoder does with the invisible part is its own business; replication keeps its residual small).
 VP8R_API int vp8r_encode_key_frames(vp8r_engine *e, int n, vp8r_stream *const *streams, const uint8_t *const *i420, int width,
-                                    int height, int q_index, int loop_filter_level, int sharpness, vp8r_frame *const *out) {
+                                    int height, int q_index, int loop_filter_level, int sharpness, unsigned flags, vp8r_frame *const *out) {
   if (!e || n <= 0 || !streams || !i420 || !out || width < 1 || height < 1 || width > 16383 || height > 16383 || q_index < 0 ||
       q_index > 127 || loop_filter_level < 0 || loop_filter_level > 63 || sharpness < 0 || sharpness > 7)
     return VP8R_ERR_INVALID_ARG;
@@ -1059,6 +1059,7 @@ VP8R_API int vp8r_encode_key_frames(vp8r_engine *e, int n, vp8r_stream *const *s
     j.key_frame = 1;
     j.lf_level = h.loop_filter_level;
     j.sharpness = h.sharpness_level;
+    j.enc_flags = uint8_t(flags);
     j.enc_src[0] = base;
     j.enc_src[1] = base + size_t(sp_y) * rows * 16;
     j.enc_src[2] = j.enc_src[1] + size_t(sp_c) * rows * 8;

@@ -101,10 +101,11 @@ class Engine:
         fa = (C.c_void_p * n)(*[f.handle for f in frames])
         check(self._lib.vp8r_reconstruct_batch(self.handle, n, sa, fa))
 
-    def encode_key_frames(self, streams, images, width, height, q_index, loop_filter_level=0, sharpness=0):
+    def encode_key_frames(self, streams, images, width, height, q_index, loop_filter_level=0, sharpness=0, bpred=True):
         """Row f4: one key frame per stream from cropped I420 images (bytes), encoded in a closed loop on the device.
         Returns the ParsedFrame objects (macroblock records + coefficient blocks; .write_bitstream() serialises them);
-        every stream then holds the reconstructed frame a decoder would produce."""
+        every stream then holds the reconstructed frame a decoder would produce.  bpred: B_PRED (sixteen 4x4 modes per
+        macroblock) competes with the four 16x16 modes (VP8R_ENC_BPRED)."""
         n = len(streams)
         need = width * height + 2 * ((width + 1) // 2) * ((height + 1) // 2)
         bufs = []
@@ -116,7 +117,7 @@ class Engine:
         sa = (C.c_void_p * n)(*[s.handle for s in streams])
         ia = (C.c_void_p * n)(*[C.cast(b, C.c_void_p) for b in bufs])
         fa = (C.c_void_p * n)(*[f.handle for f in frames])
-        check(self._lib.vp8r_encode_key_frames(self.handle, n, sa, ia, width, height, q_index, loop_filter_level, sharpness, fa))
+        check(self._lib.vp8r_encode_key_frames(self.handle, n, sa, ia, width, height, q_index, loop_filter_level, sharpness, 1 if bpred else 0, fa))
         return frames
 
     def upload(self, frame, release_host=False):
