@@ -120,8 +120,6 @@ struct SwarTune {
   int sleep_base, sleep_slope;  // ns: a waiting row sleeps base + slope * (macroblocks still missing - 1)
   int relaxed_poll;             // poll the band flag with a relaxed load, fence once it is reached
   int band_stride;              // steps between device-scope publications of a band's last row
-  int dbg_skip;                 // timing experiments only (wrong pictures): 1 = no row stores, 2 = no carry stores,
-                                // 4 = no stores of the rows above, 8 = no row loads
 };
 
 __device__ __forceinline__ int LoadFlagRelaxedSwar(const int *p) {
@@ -274,7 +272,7 @@ __device__ __forceinline__ void FilterBandSwar(const DevFrameJob *__restrict__ j
 #pragma unroll
         for (int y = 0; y < 4; ++y) W[4 + 4 * k + y] = nxt[y][k];
       const unsigned flags = flags_n;
-      if (c + 1 < cols && !(tune.dbg_skip & 8)) {
+      if (c + 1 < cols) {
 #pragma unroll
         for (int y = 0; y < 4; ++y) LoadRowWords<NB>(rowp + (ptrdiff_t)y * pitch + (c + 1) * kN, nxt[y]);
         flags_n = __ldg(&mbrow[c + 1].flags);
@@ -384,16 +382,13 @@ __device__ __forceinline__ void FilterBandSwar(const DevFrameJob *__restrict__ j
       // wait for the next left edge); whole units go out at every kG-th step, everything after the last one.
       const bool last = c == cols - 1;
       if (last || (c >= Ring::kG && c % Ring::kG == 0)) {
-        int stored;
-        if (!(tune.dbg_skip & 1)) {
-          if (last) {
-            for (int first = (c / Ring::kG) * Ring::kG - ((c % Ring::kG == 0 && c >= Ring::kG) ? Ring::kG : 0); first < cols; first += Ring::kG)
-              flush(first);
-          } else {
-            flush(c - Ring::kG);
-          }
+        if (last) {
+          for (int first = (c / Ring::kG) * Ring::kG - ((c % Ring::kG == 0 && c >= Ring::kG) ? Ring::kG : 0); first < cols; first += Ring::kG)
+            flush(first);
+        } else {
+          flush(c - Ring::kG);
         }
-        stored = last ? cols : c;
+        const int stored = last ? cols : c;
         if (last_of_band && (last || ((c / Ring::kG) % tune.band_stride) == 0)) {
           __threadfence();
           __syncwarp();
@@ -512,11 +507,10 @@ cudaError_t LaunchFilterSwar(const DevFrameJob *jobs, const FilterGroup *groups,
                              int sync_ints, cudaStream_t st) {
   if (n_groups <= 0) return cudaSuccess;
   static SwarTune tune = [] {
-    SwarTune t{400, 1500, 0, 4, 0};
+    SwarTune t{400, 1500, 0, 4};
     if (const char *v = std::getenv("VP8R_SWAR_SLEEP")) std::sscanf(v, "%d,%d", &t.sleep_base, &t.sleep_slope);
     if (const char *v = std::getenv("VP8R_SWAR_RELAXED")) t.relaxed_poll = std::atoi(v);
     if (const char *v = std::getenv("VP8R_SWAR_STRIDE")) t.band_stride = std::max(1, std::atoi(v));
-    if (const char *v = std::getenv("VP8R_SWAR_DBG_SKIP")) t.dbg_skip = std::atoi(v);
     return t;
   }();
   static const int variant = [] { const char *v = std::getenv("VP8R_SWAR_VARIANT"); return v ? std::atoi(v) : 0; }();

@@ -28,6 +28,11 @@ struct vp8r_frame {
   size_t n_mb = 0;
   // device-resident copy (owned); valid when d_blob != nullptr
   void *d_blob = nullptr;
+  // A resident frame whose parse is deferred is REWRITTEN by the parse kernels every time it is reconstructed: the
+  // engine records here the event (and its own id) after which the previous reconstruction has read the records,
+  // and lets the next parse of the same frame wait for it (replays with several batches in flight).
+  void *busy_event = nullptr;
+  unsigned long long busy_engine = 0;
   size_t d_bytes = 0;
   int d_device = -1;
   // what the engine needs on the host once the arrays live on the device (vp8r_frame_release_host):

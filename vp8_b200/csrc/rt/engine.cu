@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -103,6 +104,7 @@ struct Slot {
 
 struct vp8r_engine {
   int device = 0;
+  unsigned long long id = 0;  // process-wide serial number (vp8r_frame::busy_engine)
   cudaStream_t st = nullptr;
   bool own_stream = false;
   // Batches in flight between the host and the last kernel / packed read-backs in flight.  A batch of
@@ -510,6 +512,10 @@ VP8R_API int vp8r_engine_create(int device, void *cuda_stream, vp8r_engine **out
     return VP8R_ERR_CUDA;
   }
   vp8r_engine *e = new (std::nothrow) vp8r_engine();
+  if (e) {
+    static std::atomic<unsigned long long> serial{0};
+    e->id = ++serial;
+  }
   if (!e) return VP8R_ERR_NOMEM;
   e->device = device;
   if (const char *v = std::getenv("VP8R_INTRA_ONE_LAUNCH")) e->intra_one_launch = v[0] == '1';
@@ -775,6 +781,8 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
       const uint8_t *dev_blob;
       if (f->d_blob && f->d_device == e->device) {
         dev_blob = static_cast<const uint8_t *>(f->d_blob);
+        if (h.tokens_deferred && f->busy_event && f->busy_engine == e->id)  // its last reconstruction still reads the records
+          CU_TRY(cudaStreamWaitEvent(front, static_cast<cudaEvent_t>(f->busy_event), 0));
       } else {
         uint8_t *dst = sl.d_arena + at;
         if (f->pinned) {  // staged by the gather kernel below (SM reads of pinned memory, no copy engine)
@@ -940,6 +948,11 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
   }
   CU_TRY(cudaEventRecord(sl.done, e->st));
   sl.pending = true;
+  for (int i = 0; i < n; ++i)
+    if (frames[i]->d_blob && frames[i]->hdr.tokens_deferred) {
+      frames[i]->busy_event = sl.done;
+      frames[i]->busy_engine = e->id;
+    }
 
   // RefreshRefFrames (src/loop.h:19-46) on surface indices.
   for (int i = 0; i < n; ++i) {
