@@ -449,6 +449,74 @@ def test_token_kernel_forms_agree(engine, monkeypatch, form):
     st.close()
 
 
+def test_passes_without_draining_and_resident_replays(engine):
+    """decode(drain=False) hands the pipeline over to the next pass (new streams after reset, same ring): the frames
+    that arrive in the pinned ring are those of a drained pass.  And frames kept resident with a deferred parse
+    (their records are rewritten by the parse kernels at every reconstruction) may be replayed back to back."""
+    import ctypes as C
+    import vp8_b200
+    n, depth = 5, 3
+    ivfs = [helpers.synth_stream(f"--width 320 --height 192 --frames 7 --seed {270 + k} --log2-parts {k % 3}") for k in range(n)]
+    payloads = [vp8_b200.read_ivf(d)[1] for d in ivfs]
+    fb = 320 * 192 * 3 // 2
+    want = []
+    for p in payloads:
+        ps, orc = vp8_b200.Parser(), helpers.Oracle()
+        imgs = []
+        for x in p:
+            fr = ps.parse(x)
+            img = orc.decode(fr)
+            if fr.desc().hdr.show_frame:
+                imgs.append(img)
+            fr.close()
+        orc.close()
+        want.append(imgs)
+    bufs = [(C.c_uint8 * (n * fb))() for _ in range(depth)]
+    packed = (tuple(C.addressof(b) for b in bufs), fb)
+    dec = vp8_b200.BatchDecoder(engine, n, pinned=True, device_parse=True, depth=depth)
+    got = [[] for _ in range(n)]
+    pending = []
+
+    def on_step(t, live, frames):
+        # the ring entry of global step g is g % depth; it is complete once its ticket has been waited for
+        g = dec._g + t
+        pending.append((g, dec._tickets[g], [i for i, f in zip(live, frames) if f.desc().hdr.show_frame]))
+        while len(pending) >= depth:
+            g0, ticket, shown = pending.pop(0)
+            dec.wait(ticket)
+            for k, i in enumerate(shown):
+                got[i].append(bytes(bufs[g0 % depth][k * fb:(k + 1) * fb]))
+
+    for k in range(3):
+        dec.reset()
+        dec.decode(payloads, out_packed=packed, on_step=on_step, drain=k == 2)
+    for g0, ticket, shown in pending:
+        for k, i in enumerate(shown):
+            got[i].append(bytes(bufs[g0 % depth][k * fb:(k + 1) * fb]))
+    for i in range(n):
+        assert got[i] == want[i] * 3, f"stream {i}"
+    final_sums = engine.checksum_batch(dec.streams)
+    dec.close()
+    # resident replays: parse once with deferred modes, upload, reconstruct the same frames pass after pass
+    dec = vp8_b200.BatchDecoder(engine, n, pinned=False, device_parse=True)
+    resident = []
+    for t in range(7):
+        frames = dec.parse_into([vp8_b200.ParsedFrame(pinned=False) for _ in range(n)], [p[t] for p in payloads], list(range(n)))
+        for f in frames:
+            engine.upload(f, release_host=True)
+        resident.append(frames)
+    sums = []
+    for _ in range(4):
+        for t in range(7):
+            engine.reconstruct_batch(dec.streams, resident[t])
+        sums.append(engine.checksum_batch(dec.streams))
+    assert sums[0] == sums[1] == sums[2] == sums[3] == final_sums
+    for fr in resident:
+        for f in fr:
+            f.close()
+    dec.close()
+
+
 def test_device_parse_truncated_first_partition(engine):
     """Deferred modes: a first partition that ends early is reported by vp8r_engine_sync
     (VP8R_ERR_TRUNCATED), like the host parser does for the same bytes."""
