@@ -1036,6 +1036,7 @@ __global__ void __launch_bounds__(kFlatWarps * 32) IntraFlatKernel(const DevFram
   const DevFrameJob &job = jobs[blockIdx.y];
   if (JobFailed(job) || job.dyn || job.levels_in_one_launch || level >= job.n_intra_levels) return;  // handled by IntraLevelsKernel
   const unsigned first = __ldg(job.intra_levels + level), end = __ldg(job.intra_levels + level + 1);
+  if (first + blockIdx.x * kFlatWarps >= end) return;  // the grid is sized by the frame with most macroblocks on this level
   for (int i = threadIdx.x; i < 160; i += blockDim.x) lut[i] = c_bpred_lut[i];
   __syncthreads();
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // from lane 0: known to be warp-uniform
