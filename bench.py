@@ -459,10 +459,10 @@ def main():
     frames_per_step = S * FRAMES
     value = world * frames_per_step * args.steps / (ms / 1e3)
 
-    kern_ms = tm.ms_inter + tm.ms_intra + tm.ms_filter
+    kern_ms = tm.ms_inter + tm.ms_intra + tm.ms_filter + tm.ms_border
     peak, peak_kind = peak_hbm()
     achieved = tm.alg_bytes / (kern_ms / 1e3) / 1e9 if kern_ms > 0 else 0.0
-    shares = {"inter": tm.ms_inter, "intra": tm.ms_intra, "filter": tm.ms_filter}
+    shares = {"inter": tm.ms_inter, "intra": tm.ms_intra, "filter": tm.ms_filter, "border": tm.ms_border}
     dominant = max(shares, key=shares.get)
     n_launch = {"inter": tm.launches_inter, "intra": tm.launches_intra, "filter": tm.launches_filter}
     traffic = None
@@ -490,7 +490,7 @@ def main():
                                 "avg_launch_ms": ms_k / max(1, n_launch[name])}
     roofline["per_kernel"] = per_kernel
     roofline["secondary"] = secondary_roofline(value, world, clocks.get("sm_mhz"))
-    launches = tm.launches_inter + tm.launches_intra + tm.launches_filter
+    launches = tm.launches_inter + tm.launches_intra + 2 * tm.launches_filter  # one BorderKernel behind every filter launch
 
     # ---- end to end: compressed frames in host memory -> cropped I420 of the shown frames in pinned host memory ----
     for f in (f for fr in resident for f in fr):
@@ -590,7 +590,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "mp_per_s": e2e_value * shown_frac * W * H / 1e6, "steps": args.e2e_steps,
                     "shown_frames_per_s": e2e_value * shown_frac,
-                    "kernel_ms_per_step": (tm2.ms_inter + tm2.ms_intra + tm2.ms_filter) / max(1, args.e2e_steps + 1),
+                    "kernel_ms_per_step": (tm2.ms_inter + tm2.ms_intra + tm2.ms_filter + tm2.ms_border) / max(1, args.e2e_steps + 1),
                     "token_kernel_ms_per_step": tm2.ms_tokens / max(1, args.e2e_steps + 1),
                     "parse": args.e2e_parse, "device_header_share": device_share if args.e2e_parse == "mix" else None,
                     "steps_in_flight": DEPTH, "host_seconds_last_pass": host_seconds,

@@ -316,12 +316,13 @@ VP8R_API int vp8r_stream_decode(vp8r_stream *s, const uint8_t *data, size_t size
 typedef struct vp8r_timers {
   double ms_inter;    /* dequant+IWHT+IDCT + motion compensation of inter MBs */
   double ms_intra;    /* dequant+IWHT+IDCT + intra prediction wavefront */
-  double ms_filter;   /* loop-filter wavefront + border extension */
+  double ms_filter;   /* loop-filter wavefront */
   double ms_h2d, ms_d2h;
   double ms_tokens;   /* device-side token decode (frames with deferred tokens) */
   uint64_t launches_inter, launches_intra, launches_filter, launches_other;
   uint64_t frames, coef_blocks;
   uint64_t alg_bytes; /* sum over frames of 1.5*Wa*Ha*(1+is_inter) + 32*n_coef_blocks */
+  double ms_border;   /* border extension of the finished frames (a kernel of its own behind the loop filter) */
 } vp8r_timers;
 VP8R_API int vp8r_engine_set_timing(vp8r_engine *e, int enabled);
 VP8R_API int vp8r_engine_get_timers(vp8r_engine *e, vp8r_timers *out, int reset);

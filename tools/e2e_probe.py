@@ -39,7 +39,7 @@ for mode in MODES:
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / PASSES
         tm = eng.timers(reset=True)
-        print(f"{mode:7s} readback={rb!s:5s} {S*30/dt:8.0f} fps  wall {dt*1e3:7.0f} ms  tokens {tm.ms_tokens:6.0f} recon {tm.ms_inter+tm.ms_intra+tm.ms_filter:6.0f} h2d {tm.ms_h2d:5.0f} pack {tm.ms_d2h:5.0f}", flush=True)
+        print(f"{mode:7s} readback={rb!s:5s} {S*30/dt:8.0f} fps  wall {dt*1e3:7.0f} ms  tokens {tm.ms_tokens:6.0f} recon {tm.ms_inter+tm.ms_intra+tm.ms_filter+tm.ms_border:6.0f} h2d {tm.ms_h2d:5.0f} pack {tm.ms_d2h:5.0f}", flush=True)
         print("        host seconds:", {k: round(v, 3) for k, v in dec.host_seconds.items()}, flush=True)
         dec.close()
 eng.close()

@@ -73,9 +73,9 @@ def main():
             eng.reconstruct_batch(dec.streams, resident[t])
         tm = eng.timers(reset=True)
         out = {"streams": a.streams, "frames": a.frames, "size": a.size, "ms_inter": tm.ms_inter, "ms_intra": tm.ms_intra,
-               "ms_filter": tm.ms_filter, "ms_parse_kernels": tm.ms_tokens, "parse": a.parse, "filter_ms_per_launch": tm.ms_filter / max(1, tm.launches_filter),
+               "ms_filter": tm.ms_filter, "ms_border": tm.ms_border, "ms_parse_kernels": tm.ms_tokens, "parse": a.parse, "filter_ms_per_launch": tm.ms_filter / max(1, tm.launches_filter),
                "inter_ms_per_launch": tm.ms_inter / max(1, tm.launches_inter),
-               "frames_per_s": tm.frames / max(1e-9, (tm.ms_inter + tm.ms_intra + tm.ms_filter) / 1e3),
+               "frames_per_s": tm.frames / max(1e-9, (tm.ms_inter + tm.ms_intra + tm.ms_filter + tm.ms_border) / 1e3),
                "filter_mode": os.environ.get("VP8R_FILTER", "auto"), "wall_ms_untimed_pass": wall * 1e3,
                "wall_frames_per_s": a.streams * a.frames / wall}
     sums = eng.checksum_batch(dec.streams)

@@ -39,7 +39,7 @@ class Timers(C.Structure):
                 ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("ms_tokens", C.c_double),
                 ("launches_inter", C.c_uint64), ("launches_intra", C.c_uint64), ("launches_filter", C.c_uint64),
                 ("launches_other", C.c_uint64), ("frames", C.c_uint64), ("coef_blocks", C.c_uint64),
-                ("alg_bytes", C.c_uint64)]
+                ("alg_bytes", C.c_uint64), ("ms_border", C.c_double)]
 
 
 # name -> (restype, argtypes); mirrors include/vp8r.h one to one (tests check the two agree).

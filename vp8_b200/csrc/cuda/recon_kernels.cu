@@ -1481,9 +1481,7 @@ cudaError_t LaunchFilter(const DevFrameJob *jobs, int n_frames, int max_rows, in
                          cudaStream_t st, const FilterGroup *groups, int n_groups) {
   if (groups && n_groups > 0) {
     cudaError_t e = LaunchFilterSwar(jobs, groups, n_groups, max_rows, sync, sync_ints, st);
-    if (e != cudaSuccess) return e;
-    BorderKernel<<<dim3(8, n_frames), 256, 0, st>>>(jobs);
-    return cudaGetLastError();
+    return e;
   }
   // Bands: one warp per macroblock row (8-warp CTAs pack 4 per SM at 64 registers); with few frames
   // in the batch, thinner bands put more SMs to work.
@@ -1497,7 +1495,10 @@ cudaError_t LaunchFilter(const DevFrameJob *jobs, int n_frames, int max_rows, in
   size_t smem = ((size_t(rpb) * 4 + 15) & ~size_t(15)) + sizeof(FiltTile) * kFiltWarps;
   FilterKernel<<<n_frames * n_bands, kFiltWarps * 32, smem, st>>>(jobs, n_frames, n_bands, sync, SmCount() * kFiltCtasPerSm);
   e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  return e;
+}
+
+cudaError_t LaunchBorder(const DevFrameJob *jobs, int n_frames, cudaStream_t st) {
   BorderKernel<<<dim3(8, n_frames), 256, 0, st>>>(jobs);
   return cudaGetLastError();
 }

@@ -134,6 +134,9 @@ struct FilterGroup {
 // which has the shorter latency per frame.
 cudaError_t LaunchFilter(const DevFrameJob *jobs, int n_frames, int max_rows, int *sync, int sync_ints,
                          cudaStream_t st, const FilterGroup *groups = nullptr, int n_groups = 0);
+// Rewrites the 32-pixel border of every job's current frame (after the loop filter; next frame's motion
+// compensation reads through it).
+cudaError_t LaunchBorder(const DevFrameJob *jobs, int n_frames, cudaStream_t st);
 cudaError_t LaunchFilterSwar(const DevFrameJob *jobs, const FilterGroup *groups, int n_groups, int max_rows, int *sync,
                              int sync_ints, cudaStream_t st);
 void SwarProfDump();  // development aid, see filter_swar.cu (no-op in normal builds)

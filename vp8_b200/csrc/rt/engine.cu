@@ -411,6 +411,7 @@ void DrainTimers(vp8r_engine *e) {
         case 2: e->acc.ms_filter += ms; break;
         case 3: e->acc.ms_h2d += ms; break;
         case 5: e->acc.ms_tokens += ms; break;
+        case 6: e->acc.ms_border += ms; break;
         default: e->acc.ms_d2h += ms; break;
       }
     } else {
@@ -946,6 +947,11 @@ VP8R_API int vp8r_reconstruct_batch(vp8r_engine *e, int n, vp8r_stream *const *s
                               reinterpret_cast<const vp8r::FilterGroup *>(sl.d_jobs + n), n_groups));
     e->acc.launches_filter++;
   }
+  {
+    ScopedTimer t(e, 6);
+    CU_TRY(vp8r::LaunchBorder(sl.d_jobs, n, e->st));
+    e->acc.launches_other++;
+  }
   CU_TRY(cudaEventRecord(sl.done, e->st));
   sl.pending = true;
   for (int i = 0; i < n; ++i)
@@ -1107,6 +1113,7 @@ VP8R_API int vp8r_encode_key_frames(vp8r_engine *e, int n, vp8r_stream *const *s
     CU_TRY(vp8r::LaunchFilter(sl.d_jobs, n, rows, e->d_sync, e->sync_cap, e->st,
                               reinterpret_cast<const vp8r::FilterGroup *>(sl.d_jobs + n), n_groups));
     e->acc.launches_filter++;
+    CU_TRY(vp8r::LaunchBorder(sl.d_jobs, n, e->st));
   }
   // the arrays the bitstream writer needs
   for (int i = 0; i < n; ++i) {
