@@ -139,6 +139,30 @@ def test_native_cli_matches_golden(built, tmp_path):
         assert pos == len(data)
 
 
+@pytest.mark.parametrize("host_parse", [False, True], ids=["device-parse", "host-parse"])
+def test_native_cli_batch_mode_matches_golden(built, tmp_path, host_parse):
+    """vp8dec --batch: the lock-step loop of INTEGRATION.md written in C++ on the C ABI (frame headers on host threads,
+    everything else of the parse on the GPU unless --host-parse, packed read-back ring, fences).  Twelve vectors of
+    different lengths and sizes as twelve streams, one of them changing its size mid-stream; every shown frame against
+    the golden MD5."""
+    import subprocess
+    names = sorted(os.path.basename(v) for v in helpers.vectors())[:11] + ["vp80-05-sharpness-1439.ivf"]
+    names = list(dict.fromkeys(names))
+    out_dir = tmp_path / "out"
+    out_dir.mkdir()
+    cmd = [os.path.join(helpers.ROOT, "vp8_b200", "_lib", "vp8dec")] + (["--host-parse"] if host_parse else []) + \
+          ["--batch", str(out_dir)] + [os.path.join(helpers.VEC_DIR, n) for n in names]
+    subprocess.check_call(cmd)
+    for name in names:
+        data = (out_dir / (name + ".yuv")).read_bytes()
+        pos = 0
+        for md5, w, h in helpers.golden_md5(os.path.join(helpers.VEC_DIR, name)):
+            n = helpers.i420_bytes(w, h)
+            assert helpers.md5(data[pos:pos + n]) == md5, name
+            pos += n
+        assert pos == len(data), name
+
+
 def test_device_resident_replay_and_checksums(engine):
     """vp8r_frame_upload + vp8r_reconstruct_batch on resident frames gives the same pictures as the
     staged path, and the device checksum equals the host checksum of the copied-back frame."""
