@@ -17,6 +17,26 @@ def engine(built):
     e.close()
 
 
+@pytest.fixture(scope="module", params=["auto", "swar"])
+def engine_forms(request, built):
+    """The same tests with the loop filter the engine would pick (scalar form below 128 filtered frames per batch) and
+    with the batch form forced (FilterSwarKernel: four pixel lines per register, eight frames per warp): the engine
+    reads VP8R_FILTER when it is created."""
+    import vp8_b200
+    old = os.environ.get("VP8R_FILTER")
+    if request.param == "swar":
+        os.environ["VP8R_FILTER"] = "swar"
+    try:
+        e = vp8_b200.Engine(0)
+    finally:
+        if old is None:
+            os.environ.pop("VP8R_FILTER", None)
+        else:
+            os.environ["VP8R_FILTER"] = old
+    yield e
+    e.close()
+
+
 def first_diff(a, b):
     n = min(len(a), len(b))
     for i in range(n):
@@ -56,8 +76,9 @@ def test_stream_decode_matches_golden_and_oracle(engine, ivf):
         orc.close()
 
 
-def test_all_vectors_batched(engine):
+def test_all_vectors_batched(engine_forms):
     """BASELINE config 2: the whole suite as 43 concurrent streams, one batched launch per time step."""
+    engine = engine_forms
     import vp8_b200
     vecs = helpers.vectors()
     payloads = [vp8_b200.read_ivf(v)[1] for v in vecs]
@@ -191,10 +212,11 @@ def test_device_resident_replay_and_checksums(engine):
         f.close()
 
 
-def test_4k_frames_match_oracle_checksums(engine):
+def test_4k_frames_match_oracle_checksums(engine_forms):
     """BASELINE config 5 frame size (3840x2160, 240x135 macroblocks, 8 DCT partitions): every frame's
     device-side checksum equals the checksum of the oracle's picture, and the last frame is compared
     byte for byte."""
+    engine = engine_forms
     import vp8_b200
     ivf = helpers.synth_stream("--width 3840 --height 2160 --frames 4 --seed 51 --log2-parts 3 "
                                "--pct-skip 55 --coef-density 3 --pct-empty-block 80 --altref-period 3")
@@ -216,10 +238,11 @@ def test_4k_frames_match_oracle_checksums(engine):
         orc.close()
 
 
-def test_many_streams_lockstep_checksums(engine):
+def test_many_streams_lockstep_checksums(engine_forms):
     """48 independent streams of different seeds and two sizes in one lock-step batch (the bench's
     execution pattern, band-major filter tickets included): every stream's every frame matches the
     oracle by checksum."""
+    engine = engine_forms
     import vp8_b200
     n = 48
     ivfs = [helpers.synth_stream(f"--width {320 if k % 2 else 400} --height {240 if k % 2 else 304} --frames 5 "
@@ -250,11 +273,12 @@ def test_many_streams_lockstep_checksums(engine):
     assert got == want
 
 
-def test_randomised_streams_against_oracle(engine):
+def test_randomised_streams_against_oracle(engine_forms):
     """60 small streams with randomised generator settings (all four bitstream versions, both loop
     filters, every sharpness, 1-8 partitions, odd sizes, dense SPLIT / intra / B_PRED mixes, GOP
     lengths) decoded as one lock-step batch; every frame of every stream must equal the oracle's
     picture (device checksum vs host checksum of the oracle output)."""
+    engine = engine_forms
     import random
     import vp8_b200
     rng = random.Random(20261018)
@@ -298,9 +322,10 @@ def test_randomised_streams_against_oracle(engine):
     assert not bad, bad[:3]
 
 
-def test_packed_readback_equals_pitched_readback(engine):
+def test_packed_readback_equals_pitched_readback(engine_forms):
     """vp8r_read_batch_packed (device-side crop + I420 pack, one copy) against vp8r_stream_read_frame
     for even, odd and tiny frame sizes in one batch."""
+    engine = engine_forms
     import ctypes as C
     import vp8_b200
     sizes = [(176, 144), (175, 143), (33, 17), (16, 16), (130, 98), (320, 240)]
