@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--synth-args", default=ARGS)
     ap.add_argument("--engines", type=int, default=1, help="split the streams over this many engines (own CUDA streams), "
                     "time steps submitted round-robin: kernels of different engines overlap")
+    ap.add_argument("--serial-setup", action="store_true", help="generate the streams one after the other (under ncu the "
+                    "thread pool that runs the generator takes the process down)")
     ap.add_argument("--parse", default="host", choices=["host", "tokens", "device"],
                     help="what the replay includes: host = reconstruction kernels only; tokens = + the DCT token kernel; "
                          "device = + the macroblock-header kernel (everything behind the frame headers on the GPU)")
@@ -43,8 +45,11 @@ def main():
                                "--out", p] + a.synth_args.split())
         return vp8_b200.read_ivf(p)[1]
 
-    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
-        payloads = list(ex.map(make, range(a.streams)))
+    if a.serial_setup:
+        payloads = [make(k) for k in range(a.streams)]
+    else:
+        with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+            payloads = list(ex.map(make, range(a.streams)))
     if a.engines > 1:
         return multi_engine(a, payloads)
     eng = vp8_b200.Engine(0)
