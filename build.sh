@@ -13,7 +13,7 @@ $NVCC $ARCH -lineinfo $CXXFLAGS -Xcompiler -fPIC,-fvisibility=hidden -c vp8_b200
 $NVCC $ARCH -lineinfo $CXXFLAGS -Xcompiler -fPIC,-fvisibility=hidden -c vp8_b200/csrc/cuda/enc_kernels.cu -o vp8_b200/_build/enc_kernels.o
 $NVCC $ARCH -lineinfo $CXXFLAGS -Xcompiler -fPIC,-fvisibility=hidden -c vp8_b200/csrc/cuda/token_kernel.cu -o vp8_b200/_build/token_kernel.o
 $NVCC $ARCH -lineinfo $CXXFLAGS -Xcompiler -fPIC,-fvisibility=hidden -c vp8_b200/csrc/rt/engine.cu -o vp8_b200/_build/engine.o
-g++ -O2 -std=c++17 -Iinclude -Ivp8_b200/csrc -march=x86-64-v3 -fPIC -fvisibility=hidden -Wall -Wextra -c vp8_b200/csrc/host/frame_parser.cc -o vp8_b200/_build/frame_parser.o
+g++ -O3 -funroll-loops -std=c++17 -Iinclude -Ivp8_b200/csrc -march=x86-64-v3 -fPIC -fvisibility=hidden -Wall -Wextra -c vp8_b200/csrc/host/frame_parser.cc -o vp8_b200/_build/frame_parser.o
 g++ -O2 -std=c++17 -Iinclude -Ivp8_b200/csrc -Ivp8_b200/csrc/host -fPIC -fvisibility=hidden -Wall -Wextra -c vp8_b200/csrc/host/frame_writer.cc -o vp8_b200/_build/frame_writer.o
 g++ $CXXFLAGS -fPIC -fvisibility=hidden -Wall -Wextra -c vp8_b200/csrc/capi.cc -o vp8_b200/_build/capi.o
 $NVCC $ARCH -shared -o "$OUT/libvp8r.so" vp8_b200/_build/recon_kernels.o vp8_b200/_build/filter_swar.o vp8_b200/_build/enc_kernels.o vp8_b200/_build/token_kernel.o vp8_b200/_build/engine.o \
